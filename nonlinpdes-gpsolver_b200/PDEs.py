@@ -1,0 +1,251 @@
+"""Problem classes with the reference's names, constructor arguments, methods and attributes
+(src/PDEs.py:18-505).  The Python side only holds points, data vectors and the loop; Theta, its
+Cholesky factor, the interior block of Theta^{-1} and the GN iterate live on the GPU."""
+import numpy as onp
+from numpy import random
+
+from . import _lib
+from .sample_points import sampled_pts_rdm, sampled_pts_grid
+
+
+def eval_on_points(fun, X):
+    """vmap(fun)(X[:,0], X[:,1]) of the reference (src/PDEs.py:44-45) without JAX: try a vectorised call,
+    fall back to a per-point loop for callables that only take scalars."""
+    x1, x2 = X[:, 0], X[:, 1]
+    n = X.shape[0]
+    if n == 0:
+        return onp.zeros(0)
+    try:
+        v = onp.asarray(fun(x1, x2), dtype=onp.float64)
+        if v.shape == (n,):
+            return v
+        if v.shape == ():
+            return onp.full(n, float(v))
+    except Exception:
+        pass
+    return onp.array([float(fun(float(a), float(b))) for a, b in zip(x1, x2)], dtype=onp.float64)
+
+
+class _GPProblem(object):
+    """Shared host logic of the three PDE classes."""
+    _eqn = None            # eqn string of Gram_matrix_assembly
+    _time_dependent = False
+    _nz = 1                # number of unknown blocks
+
+    def __init__(self, bdy=None, rhs=None, domain=onp.array([[0, 1], [0, 1]])):
+        self.bdy = bdy
+        self.rhs = rhs
+        self.domain = domain
+        self._eng = None
+        self.timings = {}
+
+    # reference helpers
+    def get_bd(self, x1, x2):
+        return self.bdy(x1, x2)
+
+    def get_rhs(self, x1, x2):
+        return self.rhs(x1, x2)
+
+    def _engine(self):
+        if self._eng is None:
+            self._eng = _lib.Engine()
+        return self._eng
+
+    # ---- sampling (src/PDEs.py:34-54) ----
+    def sampled_pts(self, N_domain, N_boundary, sampled_type='random'):
+        if sampled_type == 'random':
+            X_domain, X_boundary = sampled_pts_rdm(N_domain, N_boundary, self.domain, time_dependent=self._time_dependent)
+        elif sampled_type == 'grid':
+            X_domain, X_boundary = sampled_pts_grid(N_domain, N_boundary, self.domain, time_dependent=self._time_dependent)
+        else:
+            raise ValueError(f"unknown sampled_type {sampled_type!r}")
+        self.get_sampled_points(X_domain, X_boundary)
+
+    def get_sampled_points(self, X_domain, X_boundary):
+        self.X_domain = onp.ascontiguousarray(X_domain, dtype=onp.float64)
+        self.N_domain = self.X_domain.shape[0]
+        self.X_boundary = onp.ascontiguousarray(X_boundary, dtype=onp.float64).reshape(-1, 2)
+        self.N_boundary = self.X_boundary.shape[0]
+        self.rhs_f = eval_on_points(self.get_rhs, self.X_domain)
+        self.bdy_g = eval_on_points(self.get_bd, self.X_boundary)
+        self._engine().set_points(self.X_domain, self.X_boundary)
+        self._state = 'points'
+
+    # ---- Gram matrix + nugget (src/PDEs.py:56-73, :250-269, :391-409) ----
+    def _nugget_vector(self, diag, n_blocks, nugget, nugget_type):
+        """nugget * r with r from the trace ratios of the diagonal blocks; traces are summed on the
+        host with numpy from the device-computed diagonal, like the reference's jnp/onp.trace."""
+        N, M = self.N_domain, diag.shape[0]
+        if nugget_type == 'adaptive':
+            tr = [onp.sum(diag[p * N:(p + 1) * N]) for p in range(n_blocks - 1)]
+            tr_last = onp.sum(diag[(n_blocks - 1) * N:])
+            ratio = [t / tr_last for t in tr]
+            r = onp.ones(M)
+            for p, rt in enumerate(ratio):
+                r[p * N:(p + 1) * N] = rt
+            return nugget * r, ratio
+        if nugget_type == 'identity':
+            return nugget * onp.ones(M), None
+        if nugget_type == 'none':
+            return None, None
+        raise ValueError(f"unknown nugget_type {nugget_type!r}")
+
+    def _gram(self, kernel, kernel_parameter, nugget, nugget_type):
+        eng = self._engine()
+        self.nugget_type, self.nugget = nugget_type, nugget
+        self.kernel, self.kernel_parameter = kernel, kernel_parameter
+        eng.timer_start()
+        eng.gram_assemble(0, self._eqn, kernel, kernel_parameter)
+        self.timings['assembly_ms'] = eng.timer_stop()
+        n_blocks = {'Nonlinear_elliptic': 2}.get(self._eqn, 4)
+        add, ratio = self._nugget_vector(eng.gram_get_diag(0), n_blocks, nugget, nugget_type)
+        if ratio is not None:
+            self.ratio = ratio[0] if len(ratio) == 1 else ratio
+        if add is not None:
+            eng.gram_add_diag(0, add)
+        self._state = 'gram'
+
+    # Theta / L are lazy: dense download only when somebody asks (tests, small problems)
+    @property
+    def Theta(self):
+        if self._state not in ('gram',):
+            raise RuntimeError("Theta was overwritten in place by its Cholesky factor; read it before Gram_Cholesky()")
+        return self._engine().gram_download(0, 0)
+
+    @property
+    def L(self):
+        if self._state not in ('chol', 'solved'):
+            raise RuntimeError("call Gram_Cholesky() first")
+        return self._engine().gram_download(0, 1)
+
+    def Gram_Cholesky(self):
+        """jnp.linalg.cholesky(self.Theta) (src/PDEs.py:75-80).  Like JAX, failure does not raise: the
+        factor carries NaNs and the loss turns NaN; the pivot index is kept in ``self.chol_info``."""
+        eng = self._engine()
+        eng.timer_start()
+        self.chol_info = eng.potrf(0)
+        self.timings['potrf_ms'] = eng.timer_stop()
+        self._state = 'chol'
+
+    # ---- loss / GN ----
+    def _gn_params(self):
+        raise NotImplementedError
+
+    def _setup_gn(self):
+        eng = self._engine()
+        eng.gn_setup(self._eqn, self._gn_params(), self.rhs_f, self.bdy_g)
+
+    def loss(self, z):
+        eng = self._engine()
+        self._setup_gn()
+        eng.gn_set_z(z)
+        return eng.gn_loss()
+
+    def _initial_guess(self, initial_sol):
+        n = self._nz * self.N_domain
+        if isinstance(initial_sol, str):
+            if initial_sol == 'rdm':
+                return random.normal(0.0, 1.0, (n))
+            if initial_sol == 'zero' and self._eqn == 'Eikonal':
+                return onp.zeros(n)
+            # the reference leaves `sol` undefined here and dies with a NameError
+            raise ValueError(f"initial_sol {initial_sol!r} not supported for {self._eqn}")
+        return onp.array(initial_sol, dtype=onp.float64).reshape(n)
+
+    def GN_method(self, max_iter=3, step_size=1, initial_sol='rdm', print_hist=True):
+        """src/PDEs.py:104-135 (and :309-343, :457-498).  Loop on the host, all arithmetic on the GPU;
+        one scalar (the loss) is read back per iteration because the reference prints it."""
+        eng = self._engine()
+        sol = self._initial_guess(initial_sol)
+        self.init_sol = sol
+        self._setup_gn()
+        eng.timer_start()
+        eng.inverse(0)
+        self.timings['inverse_ms'] = eng.timer_stop()
+        eng.gn_set_z(sol)
+        loss_hist = []
+        eng.timer_start()
+        loss_now = eng.gn_loss()
+        loss_hist.append(loss_now)
+        if onp.isnan(loss_now):
+            print('[Error] Loss is nan: maybe nugget is too small!')
+        if print_hist:
+            print('iter = 0', 'Loss =', loss_now)
+        for iter_step in range(1, max_iter + 1):
+            loss_now = eng.gn_step(step_size)
+            if onp.isnan(loss_now):
+                print('[Error] Loss is nan: maybe nugget is too small!')
+            loss_hist.append(loss_now)
+            if print_hist:
+                print('iter = ', iter_step, 'Gauss-Newton step size =', step_size, ' Loss = ', loss_now)
+        self.timings['gn_ms'] = eng.timer_stop()
+        self.max_iter = max_iter
+        self.step_size = step_size
+        self.loss_hist = loss_hist
+        sol = eng.gn_get_z()
+        self.sol = sol
+        self.sol_vec = eng.gn_residual(0)
+        self.sol_sampled_pts = sol[:self.N_domain]
+        self._state = 'solved'
+
+    def extend_sol(self, X_test):
+        """src/PDEs.py:203-208: Theta_test @ (L^T \\ (L \\ sol_vec)); Theta_test is never formed."""
+        eng = self._engine()
+        X_test = onp.ascontiguousarray(X_test, dtype=onp.float64)
+        temp = eng.solve_vec(0, self.sol_vec)
+        self.X_test = X_test
+        self.N_test = X_test.shape[0]
+        self.extended_sol = eng.predict(0, X_test, temp)
+
+
+class Nonlinear_elliptic2d(_GPProblem):
+    """-Delta u + alpha*u^m = f in a box (src/PDEs.py:18-208)."""
+    _eqn, _nz = 'Nonlinear_elliptic', 1
+
+    def __init__(self, alpha=1.0, m=3, bdy=None, rhs=None, domain=onp.array([[0, 1], [0, 1]])):
+        super().__init__(bdy, rhs, domain)
+        self.alpha = alpha
+        self.m = m
+
+    def _gn_params(self):
+        return [float(self.alpha), float(self.m)]
+
+    def Gram_matrix(self, kernel='Gaussian', kernel_parameter=0.2, nugget=1e-8, nugget_type='adaptive'):
+        self._gram(kernel, kernel_parameter, nugget, nugget_type)
+
+    def GN_relaxed_method(self, max_iter=3, step_size=1, initial_sol='rdm', pen_lambda=1e-10, print_hist=True):
+        raise NotImplementedError("relaxed Gauss-Newton (src/PDEs.py:137-201) is scheduled as a 'next' row (SURVEY 8f-2)")
+
+
+class Burgers(_GPProblem):
+    """u_t + alpha u u_x - nu u_xx = 0, (t, x) in [0,1] x [-1,1] (src/PDEs.py:211-350)."""
+    _eqn, _nz, _time_dependent = 'Burgers', 3, True
+
+    def __init__(self, alpha=1.0, nu=0.2, bdy=None, rhs=None, domain=onp.array([[0, 1], [-1, 1]])):
+        super().__init__(bdy, rhs, domain)
+        self.alpha = alpha
+        self.nu = nu
+
+    def _gn_params(self):
+        return [float(self.alpha), float(self.nu)]
+
+    def Gram_matrix(self, kernel='anisotropic_Gaussian', kernel_parameter=[1 / 3, 1 / 20], nugget=1e-5, nugget_type='adaptive'):
+        self._gram(kernel, kernel_parameter, nugget, nugget_type)
+
+    def GN_method(self, max_iter=10, step_size=1, initial_sol='rdm', print_hist=True):
+        super().GN_method(max_iter, step_size, initial_sol, print_hist)
+
+
+class Eikonal(_GPProblem):
+    """|grad u|^2 = f^2 + eps Delta u (src/PDEs.py:352-505)."""
+    _eqn, _nz = 'Eikonal', 3
+
+    def __init__(self, eps=3, bdy=None, rhs=None, domain=onp.array([[0, 1], [0, 1]])):
+        super().__init__(bdy, rhs, domain)
+        self.eps = eps
+
+    def _gn_params(self):
+        return [float(self.eps)]
+
+    def Gram_matrix(self, kernel='Gaussian', kernel_parameter=0.2, nugget=1e-8, nugget_type='adaptive'):
+        self._gram(kernel, kernel_parameter, nugget, nugget_type)

@@ -1,0 +1,342 @@
+// Blocked FP64 Cholesky, triangular solves and the interior block of the inverse.
+//
+// Replaces jnp.linalg.cholesky (src/PDEs.py:75-80, :271-276, :411-416;
+// src/InverseProblems.py:101-103) and the jnp.linalg.solve(L, .) calls of the GN
+// loop (src/PDEs.py:86,97,118; ...).  All O(n^3) work is routed through the
+// TMA + DMMA kernel of gemm_dmma.cu; the kernels in this file are the small
+// O(n^2 nb) pieces: 64x64 diagonal factorisations, 64-wide triangular solves by
+// substitution (no explicit inverses: nuggets down to 1e-13 leave no slack) and
+// the vector triangular solves.
+#include "gpp_internal.cuh"
+
+namespace {
+
+constexpr int BASE = 64;
+constexpr int LDS_PAD = BASE + 1;
+
+// ---------------------------------------------------------------------------
+// potrf of one diagonal block (n <= 64) held in shared memory, right-looking.
+// A non-positive / NaN pivot is recorded once in *info (1-based global index);
+// sqrt then produces NaN which propagates, like jnp.linalg.cholesky's NaN output.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+potrf_base_kernel(double* __restrict__ A, long ld, int n, int gidx0, int* info) {
+  __shared__ double s[BASE * LDS_PAD];
+  const int tid = threadIdx.x;
+  for (int e = tid; e < n * n; e += blockDim.x) {
+    int i = e / n, j = e % n;
+    if (j <= i) s[i * LDS_PAD + j] = A[(long)i * ld + j];
+  }
+  __syncthreads();
+  for (int j = 0; j < n; ++j) {
+    if (tid == 0) {
+      double d = s[j * LDS_PAD + j];
+      if (!(d > 0.0)) atomicCAS(info, 0, gidx0 + j + 1);
+      s[j * LDS_PAD + j] = sqrt(d);
+    }
+    __syncthreads();
+    const double djj = s[j * LDS_PAD + j];
+    for (int i = j + 1 + tid; i < n; i += blockDim.x) s[i * LDS_PAD + j] = s[i * LDS_PAD + j] / djj;
+    __syncthreads();
+    // trailing rank-1 update of the lower triangle
+    const int rem = n - j - 1;
+    for (int e = tid; e < rem * rem; e += blockDim.x) {
+      int i = j + 1 + e / rem, k = j + 1 + e % rem;
+      if (k <= i) s[i * LDS_PAD + k] = fma(-s[i * LDS_PAD + j], s[k * LDS_PAD + j], s[i * LDS_PAD + k]);
+    }
+    __syncthreads();
+  }
+  for (int e = tid; e < n * n; e += blockDim.x) {
+    int i = e / n, j = e % n;
+    if (j <= i) A[(long)i * ld + j] = s[i * LDS_PAD + j];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// X * L^T = P  for an nb x nb (nb <= 64) lower-triangular L, P is rows x nb, in place.
+// One thread per row, substitution along the row:  x_j = (p_j - sum_{k<j} x_k L_jk) / L_jj.
+// ---------------------------------------------------------------------------
+constexpr int TRSM_ROWS = 128;
+__global__ void __launch_bounds__(TRSM_ROWS)
+trsm_base_kernel(double* __restrict__ P, long ldp, int rows, const double* __restrict__ L, long ldl, int nb) {
+  extern __shared__ double sm[];
+  double* sL = sm;                       // nb x LDS_PAD
+  double* sP = sm + BASE * LDS_PAD;      // TRSM_ROWS x LDS_PAD
+  const int tid = threadIdx.x;
+  const int r0 = blockIdx.x * TRSM_ROWS;
+  for (int e = tid; e < nb * nb; e += blockDim.x) {
+    int i = e / nb, j = e % nb;
+    sL[i * LDS_PAD + j] = (j <= i) ? L[(long)i * ldl + j] : 0.0;
+  }
+  const int nrow = min(TRSM_ROWS, rows - r0);
+  for (int e = tid; e < nrow * nb; e += blockDim.x) {
+    int i = e / nb, j = e % nb;
+    sP[i * LDS_PAD + j] = P[(long)(r0 + i) * ldp + j];
+  }
+  __syncthreads();
+  if (tid < nrow) {
+    double* x = sP + tid * LDS_PAD;
+    for (int j = 0; j < nb; ++j) {
+      double acc = x[j];
+      const double* lj = sL + j * LDS_PAD;
+      for (int k = 0; k < j; ++k) acc = fma(-x[k], lj[k], acc);
+      x[j] = acc / lj[j];
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < nrow * nb; e += blockDim.x) {
+    int i = e / nb, j = e % nb;
+    P[(long)(r0 + i) * ldp + j] = sP[i * LDS_PAD + j];
+  }
+}
+
+__global__ void fill_identity_kernel(double* __restrict__ A, long ld, int rows, int cols) {
+  long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < (long)rows * cols) {
+    int i = (int)(e / cols), j = (int)(e % cols);
+    A[(long)i * ld + j] = (i == j) ? 1.0 : 0.0;
+  }
+}
+
+// mirror the lower triangle of an n x n matrix into its upper triangle (32x32 smem transpose)
+__global__ void symmetrize_kernel(double* __restrict__ A, long ld, int n) {
+  __shared__ double tile[32][33];
+  const int bi = blockIdx.y, bj = blockIdx.x;   // block row / col, bj <= bi processed
+  if (bj > bi) return;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  for (int k = ty; k < 32; k += 8) {
+    int r = bi * 32 + k, c = bj * 32 + tx;
+    tile[k][tx] = (r < n && c < n) ? A[(long)r * ld + c] : 0.0;
+  }
+  __syncthreads();
+  for (int k = ty; k < 32; k += 8) {
+    int r = bj * 32 + k, c = bi * 32 + tx;   // transposed position
+    if (r < n && c < n && c > r) A[(long)r * ld + c] = tile[tx][k];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// vector triangular solves, 64-wide blocks
+// ---------------------------------------------------------------------------
+// solve the diagonal block in place: forward (L x = b) or backward (L^T x = b)
+__global__ void __launch_bounds__(BASE)
+trsv_diag_kernel(const double* __restrict__ L, long ld, int nb, double* __restrict__ x, int transposed) {
+  __shared__ double s[BASE * LDS_PAD];
+  __shared__ double xs[BASE];
+  const int tid = threadIdx.x;
+  for (int e = tid; e < nb * nb; e += blockDim.x) {
+    int i = e / nb, j = e % nb;
+    if (j <= i) s[i * LDS_PAD + j] = L[(long)i * ld + j];
+  }
+  if (tid < nb) xs[tid] = x[tid];
+  __syncthreads();
+  if (!transposed) {
+    for (int j = 0; j < nb; ++j) {
+      if (tid == j) xs[j] = xs[j] / s[j * LDS_PAD + j];
+      __syncthreads();
+      if (tid > j && tid < nb) xs[tid] = fma(-s[tid * LDS_PAD + j], xs[j], xs[tid]);
+      __syncthreads();
+    }
+  } else {
+    for (int j = nb - 1; j >= 0; --j) {
+      if (tid == j) xs[j] = xs[j] / s[j * LDS_PAD + j];
+      __syncthreads();
+      if (tid < j) xs[tid] = fma(-s[j * LDS_PAD + tid], xs[j], xs[tid]);
+      __syncthreads();
+    }
+  }
+  if (tid < nb) x[tid] = xs[tid];
+}
+
+// forward update: x[r] -= sum_k L[r][k] xb[k] for r in the rows below the block; 16 lanes per row
+__global__ void __launch_bounds__(256)
+trsv_fwd_update_kernel(const double* __restrict__ Lpanel, long ld, int rows, int nb,
+                       const double* __restrict__ xb, double* __restrict__ x) {
+  __shared__ double sx[BASE];
+  if (threadIdx.x < BASE) sx[threadIdx.x] = threadIdx.x < nb ? xb[threadIdx.x] : 0.0;
+  __syncthreads();
+  const int sub = threadIdx.x & 15;
+  const long r = (long)blockIdx.x * 16 + (threadIdx.x >> 4);
+  double acc = 0.0;
+  if (r < rows) {
+    const double* row = Lpanel + r * ld;
+    for (int k = sub; k < nb; k += 16) acc = fma(row[k], sx[k], acc);
+  }
+#pragma unroll
+  for (int o = 8; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, 16);
+  if (r < rows && sub == 0) x[r] -= acc;
+}
+
+// backward update: x[c] -= sum_k L[k][c] xb[k] for columns c left of the block; one thread per column
+__global__ void __launch_bounds__(256)
+trsv_bwd_update_kernel(const double* __restrict__ Lrows, long ld, int cols, int nb,
+                       const double* __restrict__ xb, double* __restrict__ x) {
+  __shared__ double sx[BASE];
+  if (threadIdx.x < BASE) sx[threadIdx.x] = threadIdx.x < nb ? xb[threadIdx.x] : 0.0;
+  __syncthreads();
+  const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  double acc = 0.0;
+  for (int k = 0; k < nb; ++k) acc = fma(Lrows[(long)k * ld + c], sx[k], acc);
+  x[c] -= acc;
+}
+
+struct Mat {
+  double* base;
+  long ld;
+  const CUtensorMap* map;
+};
+
+int trsm_right_lt(gpp_handle* h, const Mat& P, int pr0, int pc0, int rows, const Mat& L, int l0, int nb) {
+  if (rows <= 0 || nb <= 0) return GPP_OK;
+  if (nb <= BASE) {
+    static bool attr = false;
+    const int smem = (BASE * LDS_PAD + TRSM_ROWS * LDS_PAD) * 8;
+    if (!attr) {
+      CUDA_TRY(h, cudaFuncSetAttribute(trsm_base_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      attr = true;
+    }
+    trsm_base_kernel<<<(rows + TRSM_ROWS - 1) / TRSM_ROWS, TRSM_ROWS, smem, h->stream>>>(
+        P.base + (long)pr0 * P.ld + pc0, P.ld, rows, L.base + (long)l0 * L.ld + l0, L.ld, nb);
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    return GPP_OK;
+  }
+  const int hh = (int)round_up((nb + 1) / 2, BASE);
+  int rc = trsm_right_lt(h, P, pr0, pc0, rows, L, l0, hh);
+  if (rc) return rc;
+  GemmDesc d{};
+  d.mapA = P.map; d.mapB = L.map; d.mapAdiag = nullptr; d.mapBdiag = nullptr;
+  d.a_row0 = pr0; d.b_row0 = l0 + hh;
+  d.C = P.base + (long)pr0 * P.ld + pc0 + hh; d.ldc = P.ld;
+  d.Cin = d.C; d.ldcin = P.ld;
+  d.m = rows; d.n = nb - hh;
+  d.k0 = pc0; d.k1 = pc0 + hh; d.kb_off = l0 - pc0;
+  d.ktri = 0; d.diag_nb = 0; d.alpha = -1.0; d.lower_only = 0;
+  rc = gemm_nt_launch(h, d);
+  if (rc) return rc;
+  return trsm_right_lt(h, P, pr0, pc0 + hh, rows, L, l0 + hh, nb - hh);
+}
+
+int potrf_diag(gpp_handle* h, const Mat& A, int o, int nb, int gidx0) {
+  if (nb <= BASE) {
+    potrf_base_kernel<<<1, 256, 0, h->stream>>>(A.base + (long)o * A.ld + o, A.ld, nb, gidx0, h->d_info);
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    return GPP_OK;
+  }
+  const int hh = (int)round_up((nb + 1) / 2, BASE);
+  int rc = potrf_diag(h, A, o, hh, gidx0);
+  if (rc) return rc;
+  rc = trsm_right_lt(h, A, o + hh, o, nb - hh, A, o, hh);
+  if (rc) return rc;
+  GemmDesc d{};
+  d.mapA = A.map; d.mapB = A.map;
+  d.a_row0 = o + hh; d.b_row0 = o + hh;
+  d.C = A.base + (long)(o + hh) * A.ld + o + hh; d.ldc = A.ld; d.Cin = d.C; d.ldcin = A.ld;
+  d.m = nb - hh; d.n = nb - hh; d.k0 = o; d.k1 = o + hh; d.kb_off = 0;
+  d.alpha = -1.0; d.lower_only = 1;
+  rc = gemm_nt_launch(h, d);
+  if (rc) return rc;
+  return potrf_diag(h, A, o + hh, nb - hh, gidx0 + hh);
+}
+
+}  // namespace
+
+// Left-looking blocked Cholesky: block column j first receives all earlier updates in one
+// long-K GEMM (accumulators stay in registers, the block column is read and written once),
+// then its diagonal block is factorised and the rows below are solved against it.
+int potrf_lower(gpp_handle* h, double* A, long ld, int n, const CUtensorMap* map) {
+  Mat M{A, ld, map};
+  const int NB = h->NB;
+  CUDA_TRY(h, cudaMemsetAsync(h->d_info, 0, sizeof(int), h->stream));
+  for (int j0 = 0; j0 < n; j0 += NB) {
+    const int nbj = (n - j0 < NB) ? (n - j0) : NB;
+    if (j0 > 0) {
+      GemmDesc d{};
+      d.mapA = map; d.mapB = map;
+      d.a_row0 = j0; d.b_row0 = j0;
+      d.C = A + (long)j0 * ld + j0; d.ldc = ld; d.Cin = d.C; d.ldcin = ld;
+      d.m = n - j0; d.n = nbj; d.k0 = 0; d.k1 = j0; d.kb_off = 0;
+      d.alpha = -1.0; d.lower_only = 0;
+      int rc = gemm_nt_launch(h, d);
+      if (rc) return rc;
+    }
+    int rc = potrf_diag(h, M, j0, nbj, j0);
+    if (rc) return rc;
+    rc = trsm_right_lt(h, M, j0 + nbj, j0, n - j0 - nbj, M, j0, nbj);
+    if (rc) return rc;
+  }
+  return GPP_OK;
+}
+
+// U = L^{-T} (block column by block column, into the strict upper triangle of the buffer,
+// clean diagonal blocks in udiag), then Ainv = (U U^T)[0:Mint, 0:Mint] = (Theta^{-1}) interior block.
+int inverse_interior(gpp_handle* h, GramSlot& s) {
+  const int NB = h->NB, M = s.M;
+  Mat T{s.T, s.ld, &s.mapT};
+  Mat UD{s.udiag, (long)NB, &s.mapUdiag};
+  for (int o = 0; o < M; o += NB) {
+    const int nbi = (M - o < NB) ? (M - o) : NB;
+    {
+      long tot = (long)NB * NB;
+      fill_identity_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(s.udiag + (long)o * NB, NB, NB, NB);
+      h->launches++;
+    }
+    int rc = trsm_right_lt(h, UD, o, 0, nbi, T, o, nbi);   // X L_ii^T = I
+    if (rc) return rc;
+    if (o > 0) {
+      GemmDesc d{};
+      d.mapA = &s.mapT; d.mapAdiag = &s.mapUdiag; d.mapB = &s.mapT; d.mapBdiag = nullptr;
+      d.a_row0 = 0; d.b_row0 = o;
+      d.C = s.T + o; d.ldc = s.ld; d.Cin = nullptr; d.ldcin = 0;
+      d.m = o; d.n = nbi; d.k0 = 0; d.k1 = o; d.kb_off = 0;
+      d.ktri = 1; d.diag_nb = NB; d.alpha = -1.0; d.lower_only = 0;
+      rc = gemm_nt_launch(h, d);
+      if (rc) return rc;
+      rc = trsm_right_lt(h, T, 0, o, o, T, o, nbi);
+      if (rc) return rc;
+    }
+  }
+  {
+    GemmDesc d{};
+    d.mapA = &s.mapT; d.mapAdiag = &s.mapUdiag; d.mapB = &s.mapT; d.mapBdiag = &s.mapUdiag;
+    d.a_row0 = 0; d.b_row0 = 0;
+    d.C = s.Ainv; d.ldc = s.ldA; d.Cin = nullptr;
+    d.m = s.Mint; d.n = s.Mint; d.k0 = 0; d.k1 = (int)round_up(M, 16); d.kb_off = 0;
+    d.ktri = 1; d.diag_nb = NB; d.alpha = 1.0; d.lower_only = 1;
+    int rc = gemm_nt_launch(h, d);
+    if (rc) return rc;
+    dim3 grid((s.Mint + 31) / 32, (s.Mint + 31) / 32), blk(32, 8);
+    symmetrize_kernel<<<grid, blk, 0, h->stream>>>(s.Ainv, s.ldA, s.Mint);
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+  }
+  return GPP_OK;
+}
+
+int trsv_lower(gpp_handle* h, const double* L, long ld, int n, double* x, bool transposed) {
+  if (!transposed) {
+    for (int j0 = 0; j0 < n; j0 += BASE) {
+      const int nb = (n - j0 < BASE) ? (n - j0) : BASE;
+      trsv_diag_kernel<<<1, BASE, 0, h->stream>>>(L + (long)j0 * ld + j0, ld, nb, x + j0, 0);
+      const int rows = n - j0 - nb;
+      if (rows > 0)
+        trsv_fwd_update_kernel<<<(rows + 15) / 16, 256, 0, h->stream>>>(L + (long)(j0 + nb) * ld + j0, ld, rows, nb,
+                                                                         x + j0, x + j0 + nb);
+      h->launches += 2;
+    }
+  } else {
+    const int nblk = (n + BASE - 1) / BASE;
+    for (int b = nblk - 1; b >= 0; --b) {
+      const int j0 = b * BASE;
+      const int nb = (n - j0 < BASE) ? (n - j0) : BASE;
+      trsv_diag_kernel<<<1, BASE, 0, h->stream>>>(L + (long)j0 * ld + j0, ld, nb, x + j0, 1);
+      if (j0 > 0)
+        trsv_bwd_update_kernel<<<(j0 + 255) / 256, 256, 0, h->stream>>>(L + (long)j0 * ld, ld, j0, nb, x + j0, x);
+      h->launches += 2;
+    }
+  }
+  CUDA_TRY(h, cudaGetLastError());
+  return GPP_OK;
+}

@@ -1,0 +1,265 @@
+// FP64 "NT" GEMM / SYRK on sm_100a:  C = Cin + alpha * A * B^T  with A (m x K) and
+// B (n x K) both row-major (K contiguous).  This one kernel carries every O(M^3) part
+// of the hot path (reference: jnp.linalg.cholesky src/PDEs.py:77, the L^{-1}J solves
+// and J^T Theta^{-1} J products of src/PDEs.py:97-102): left-looking Cholesky updates,
+// the triangular-inverse updates and the U U^T product.
+//
+// Design (B200): tcgen05 has no FP64 kind, so FP64 tensor work is mma.sync m8n8k4
+// (SASS DMMA.8x8x4, measured pipe peak 37.0 TFLOP/s, profiles/r01_fp64_pipe_microbench.txt)
+// with register accumulators.  Operand tiles (128 rows x 16 k) are brought in by TMA
+// (cp.async.bulk.tensor.2d, 128B swizzle) into a 4-stage mbarrier ring by one
+// producer warp; 16 consumer warps each own a 32x32 block of the 128x128 CTA tile.
+// The k-slot -> column mapping inside a 16-wide chunk is permuted (same for A and B)
+// so that every fragment load is a conflict-free LDS.64 under the 128B swizzle.
+#include "gpp_internal.cuh"
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 16, STAGES = 6;
+constexpr int CONSUMER_WARPS = 16;
+constexpr int THREADS = (CONSUMER_WARPS + 1) * 32;
+constexpr int TILE_BYTES = BM * BK * 8;           // 16 KB per operand tile
+constexpr int STAGE_BYTES = 2 * TILE_BYTES;       // A + B
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+struct GemmParams {
+  CUtensorMap mapA, mapB, mapAdiag, mapBdiag;
+  int has_adiag, has_bdiag;
+  int a_row0, b_row0;
+  double* C; long ldc;
+  const double* Cin; long ldcin;
+  int m, n, k0, k1, kb_off, ktri, diag_nb;
+  double alpha;
+  int lower_only;
+  int tiles_m, tiles_n;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ double lds64(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_nt_dmma_kernel(const __grid_constant__ GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // 1024B alignment for the 128B swizzle atom
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+
+  // tile index -> (tm, tn); lower_only enumerates the lower-triangular tile set row by row
+  int tm, tn;
+  if (p.lower_only) {
+    // tiles (i, j) with j <= i + shift where shift accounts for a_row0/b_row0 offsets being equal
+    long t = blockIdx.x;
+    int i = static_cast<int>((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while ((long)(i + 1) * (i + 2) / 2 <= t) ++i;
+    while ((long)i * (i + 1) / 2 > t) --i;
+    tm = i;
+    tn = static_cast<int>(t - (long)i * (i + 1) / 2);
+  } else {
+    tm = blockIdx.x / p.tiles_n;
+    tn = blockIdx.x % p.tiles_n;
+  }
+  const int row_base = tm * BM;    // within the output block
+  const int col_base = tn * BN;
+  const int a_row = p.a_row0 + row_base;
+  const int b_row = p.b_row0 + col_base;
+
+  int k_lo = p.k0;
+  if (p.ktri) {
+    int kb = (a_row / p.diag_nb) * p.diag_nb;
+    if (kb > k_lo) k_lo = kb;
+  }
+  const int nchunks = (p.k1 > k_lo) ? (p.k1 - k_lo + BK - 1) / BK : 0;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CONSUMER_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == CONSUMER_WARPS) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      const int a_dblk = a_row / p.diag_nb, b_dblk = b_row / p.diag_nb;
+      for (int c = 0; c < nchunks; ++c) {
+        const int s = c % STAGES;
+        const uint32_t ph = (c / STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        uint8_t* sa = smem + s * STAGE_BYTES;
+        uint8_t* sb = sa + TILE_BYTES;
+        mbar_expect_tx(&full[s], STAGE_BYTES);
+        const int k = k_lo + c * BK;
+        const int kblk = k / p.diag_nb;
+        if (p.has_adiag && kblk == a_dblk) tma_load_2d(sa, &p.mapAdiag, &full[s], k - kblk * p.diag_nb, a_row);
+        else tma_load_2d(sa, &p.mapA, &full[s], k, a_row);
+        if (p.has_bdiag && kblk == b_dblk) tma_load_2d(sb, &p.mapBdiag, &full[s], k - kblk * p.diag_nb, b_row);
+        else tma_load_2d(sb, &p.mapB, &full[s], k + p.kb_off, b_row);
+      }
+    }
+    return;
+  }
+
+  // ===== consumers: 16 warps, 4 (m) x 4 (n), each 32 x 32 =====
+  const int wm = warp >> 2, wn = warp & 3;
+  const int g = lane >> 2, t = lane & 3;
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  // per-thread swizzled offsets: step s reads logical 16B chunk (s + 4*(t>>1)), element t&1
+  uint32_t koff[4];
+#pragma unroll
+  for (int s = 0; s < 4; ++s) koff[s] = ((((s + 4 * (t >> 1)) ^ g) << 4) + ((t & 1) << 3));
+  const uint32_t a_thr = (wm * 32 + g) * 128;
+  const uint32_t b_thr = (wn * 32 + g) * 128;
+  const uint32_t smem_base = smem_u32(smem);
+
+  for (int c = 0; c < nchunks; ++c) {
+    const int s = c % STAGES;
+    const uint32_t ph = (c / STAGES) & 1;
+    mbar_wait(&full[s], ph);
+    const uint32_t sa = smem_base + s * STAGE_BYTES + a_thr;
+    const uint32_t sb = smem_base + s * STAGE_BYTES + TILE_BYTES + b_thr;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = lds64(sa + i * 1024 + koff[ks]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = lds64(sb + j * 1024 + koff[ks]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+  }
+
+  // ===== epilogue: C = Cin + alpha * acc =====
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = row_base + wm * 32 + i * 8 + g;
+    if (r >= p.m) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int cc = col_base + wn * 32 + j * 8 + 2 * t;
+      if (cc >= p.n) continue;
+      double v0 = p.alpha * acc[i][j][0], v1 = p.alpha * acc[i][j][1];
+      double* dst = p.C + (long)r * p.ldc + cc;
+      const bool two = (cc + 1 < p.n);
+      if (p.Cin) {
+        const double* src = p.Cin + (long)r * p.ldcin + cc;
+        v0 += src[0];
+        if (two) v1 += src[1];
+      }
+      if (two && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+        *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
+      } else {
+        dst[0] = v0;
+        if (two) dst[1] = v1;
+      }
+    }
+  }
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled g_encode = nullptr;
+
+}  // namespace
+
+int make_tensor_map(gpp_handle* h, CUtensorMap* map, const double* base, long rows, long cols, long ld) {
+  if (!g_encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CUDA_TRY(h, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) { h->err = "cuTensorMapEncodeTiled not available"; return GPP_CUDA_ERR; }
+    g_encode = reinterpret_cast<PFN_encodeTiled>(fn);
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || ((ld * 8) & 15)) { h->err = "tensor map: base/stride not 16B aligned"; return -1; }
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 8};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { h->err = "cuTensorMapEncodeTiled failed: " + std::to_string((int)r); return GPP_CUDA_ERR; }
+  return GPP_OK;
+}
+
+int gemm_nt_launch(gpp_handle* h, const GemmDesc& d) {
+  if (d.m <= 0 || d.n <= 0) return GPP_OK;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(h, cudaFuncSetAttribute(gemm_nt_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  GemmParams p;
+  p.mapA = *d.mapA;
+  p.mapB = *d.mapB;
+  p.has_adiag = d.mapAdiag != nullptr;
+  p.has_bdiag = d.mapBdiag != nullptr;
+  p.mapAdiag = d.mapAdiag ? *d.mapAdiag : *d.mapA;
+  p.mapBdiag = d.mapBdiag ? *d.mapBdiag : *d.mapB;
+  p.a_row0 = d.a_row0; p.b_row0 = d.b_row0;
+  p.C = d.C; p.ldc = d.ldc; p.Cin = d.Cin; p.ldcin = d.ldcin;
+  p.m = d.m; p.n = d.n; p.k0 = d.k0; p.k1 = d.k1; p.kb_off = d.kb_off; p.ktri = d.ktri;
+  p.diag_nb = d.diag_nb > 0 ? d.diag_nb : (1 << 30);
+  p.alpha = d.alpha; p.lower_only = d.lower_only;
+  p.tiles_m = (d.m + BM - 1) / BM;
+  p.tiles_n = (d.n + BN - 1) / BN;
+  long ntiles;
+  if (d.lower_only) {
+    // square lower-triangular tile set (requires a_row0 == b_row0 and m == n)
+    ntiles = (long)p.tiles_m * (p.tiles_m + 1) / 2;
+  } else {
+    ntiles = (long)p.tiles_m * p.tiles_n;
+  }
+  gemm_nt_dmma_kernel<<<(unsigned)ntiles, THREADS, SMEM_BYTES, h->stream>>>(p);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return GPP_OK;
+}

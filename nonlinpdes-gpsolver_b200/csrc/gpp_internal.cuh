@@ -1,0 +1,160 @@
+// Internal declarations shared by the translation units of libgpp_b200.so.
+// Everything here is device-side plumbing for the GP-PDE Gauss-Newton hot path
+// (Gram assembly -> Cholesky -> GN steps); the public C ABI is include/gpp.h.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#define GPP_MAX_SLOTS 2      // Darcy needs Theta_u and Theta_a
+#define GPP_MAX_BLOCKS 4     // row-operator blocks per Gram matrix
+#define GPP_MAX_ZBLOCKS 6    // unknown blocks (Darcy: w0 w1 w2 v0 v1 v2)
+
+// row operators (src/Gram_matrice.py block layouts)
+enum { OP_ID = 0, OP_D1 = 1, OP_D2 = 2, OP_D22 = 3, OP_LAP = 4 };
+// layouts
+enum { LAY_ELLIPTIC = 0, LAY_BURGERS = 1, LAY_EIKONAL = 2, LAY_DARCY_A = 3 };
+// PDE ids for the GN step
+enum { PDE_ELLIPTIC = 0, PDE_BURGERS = 1, PDE_EIKONAL = 2, PDE_DARCY = 3 };
+
+struct Layout {
+  int nblk;
+  int op[GPP_MAX_BLOCKS];
+  int with_bdy[GPP_MAX_BLOCKS];
+};
+
+inline Layout make_layout(int id) {
+  Layout l{};
+  switch (id) {
+    case LAY_ELLIPTIC: l.nblk = 2; l.op[0] = OP_LAP; l.op[1] = OP_ID; l.with_bdy[1] = 1; break;
+    case LAY_BURGERS:  l.nblk = 4; l.op[0] = OP_D1; l.op[1] = OP_D2; l.op[2] = OP_D22; l.op[3] = OP_ID; l.with_bdy[3] = 1; break;
+    case LAY_EIKONAL:  l.nblk = 4; l.op[0] = OP_D1; l.op[1] = OP_D2; l.op[2] = OP_LAP; l.op[3] = OP_ID; l.with_bdy[3] = 1; break;
+    case LAY_DARCY_A:  l.nblk = 3; l.op[0] = OP_D1; l.op[1] = OP_D2; l.op[2] = OP_ID; break;
+    default: l.nblk = 0;
+  }
+  return l;
+}
+
+// One Gram system: Theta -> L (lower triangle, in place), U = L^{-T} (strict upper
+// triangle of the same buffer + clean diagonal blocks in udiag), Ainv = interior
+// block of Theta^{-1} (full symmetric, separate buffer).
+struct GramSlot {
+  int layout_id = -1;
+  Layout lay{};
+  int N = 0, Nb = 0, M = 0, Mint = 0;   // Mint = rows that J touches (all but boundary rows)
+  int off[GPP_MAX_BLOCKS + 1] = {0};
+  long ld = 0;                           // leading dimension (doubles), multiple of 16
+  double* T = nullptr;                   // M x ld
+  double* udiag = nullptr;               // (nblk*NB) x NB clean diagonal blocks of U
+  double* Ainv = nullptr;                // Mint x ldA
+  long ldA = 0;
+  bool factored = false, inverted = false;
+  CUtensorMap mapT, mapUdiag;            // TMA descriptors (box 16 x 128 doubles, 128B swizzle)
+  double kp_b1 = 0, kp_b2 = 0;           // kernel scales b1, b2
+  double kp_e1 = 0, kp_e2 = 0;           // exponent coefficients (see gram.cu)
+  int kernel_id = 0;
+};
+
+struct GnState {
+  int pde = -1;
+  int nz = 0;                 // number of unknown blocks
+  int n = 0;                  // nz * N
+  double params[4] = {0};
+  int m_int = 0;              // elliptic: integer exponent m (0 if non-integer)
+  double* rhs_f = nullptr;    // N
+  double* bdy_g = nullptr;    // Nb
+  double* data_u = nullptr;   // N_data
+  int N_data = 0;
+  double noise = 1.0;
+  double* z = nullptr;        // n
+  double* F[GPP_MAX_SLOTS] = {nullptr, nullptr};     // M_s
+  double* s[GPP_MAX_SLOTS] = {nullptr, nullptr};     // L^{-1} F
+  double* t[GPP_MAX_SLOTS] = {nullptr, nullptr};     // L^{-T} L^{-1} F
+  double* coef = nullptr;     // [slot][p][q][N] Jacobian coefficient vectors
+  unsigned char coef_kind[GPP_MAX_SLOTS][GPP_MAX_BLOCKS][GPP_MAX_ZBLOCKS]; // 0 zero, 1 vector
+  double* H = nullptr;        // n x ldH
+  long ldH = 0;
+  double* g = nullptr;        // n
+  double* scal = nullptr;     // small device scratch for reductions
+  CUtensorMap mapH;
+  bool ready = false;
+};
+
+struct gpp_handle {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int N = 0, Nb = 0;
+  double* Xd = nullptr;       // N x 2
+  double* Xb = nullptr;       // Nb x 2
+  double* Xall = nullptr;     // (N+Nb) x 2 : interior then boundary
+  GramSlot slot[GPP_MAX_SLOTS];
+  GnState gn;
+  int* d_info = nullptr;      // device flag: first failed pivot (1-based) or 0
+  double* work = nullptr;     // scratch (panel copies)
+  size_t work_bytes = 0;
+  int NB = 512;               // block-column width of the blocked factorisations
+  // timing
+  cudaEvent_t ev[8];
+  float t_asm = 0, t_potrf = 0, t_inv = 0, t_step = 0;
+  long launches = 0;
+  // distributed (dist.cu)
+  void* dist = nullptr;
+};
+
+#define GPP_OK 0
+#define GPP_CUDA_ERR 1000
+
+#define CUDA_TRY(h, expr)                                                         \
+  do {                                                                            \
+    cudaError_t _e = (expr);                                                      \
+    if (_e != cudaSuccess) {                                                      \
+      (h)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);              \
+      return GPP_CUDA_ERR;                                                        \
+    }                                                                             \
+  } while (0)
+
+static inline long round_up(long x, long m) { return (x + m - 1) / m * m; }
+
+// ---- gemm_dmma.cu -----------------------------------------------------------
+struct GemmDesc {
+  const CUtensorMap* mapA;      // operand A rows (K-contiguous)
+  const CUtensorMap* mapB;      // operand B rows (K-contiguous)
+  const CUtensorMap* mapAdiag;  // optional clean diagonal blocks for A (U operand), else null
+  const CUtensorMap* mapBdiag;  // optional clean diagonal blocks for B
+  int a_row0, b_row0;           // first row of A / B operand (map coordinates)
+  double* C; long ldc;          // output origin pointer (row-major), already offset
+  const double* Cin; long ldcin;// optional addend (may alias C), already offset
+  int m, n;                     // output extents
+  int k0, k1;                   // K range in A-map column coordinates
+  int kb_off;                   // B-map column = k + kb_off
+  int ktri;                     // 1: A rows are upper-triangular: k starts at diag block of the row tile
+  int diag_nb;                  // block size of the clean diagonal blocks (NB)
+  double alpha;
+  int lower_only;               // skip tiles strictly above the diagonal (uses global row/col = a_row0+i, b_row0+j)
+};
+int gemm_nt_launch(gpp_handle* h, const GemmDesc& d);
+int make_tensor_map(gpp_handle* h, CUtensorMap* map, const double* base, long rows, long cols, long ld);
+
+// ---- chol.cu ---------------------------------------------------------------
+// Blocked lower Cholesky of the n x n matrix at A (row-major, ld), in place, using map for TMA.
+int potrf_lower(gpp_handle* h, double* A, long ld, int n, const CUtensorMap* map);
+// U = L^{-T} into the strict upper triangle + udiag, then Ainv = (L L^T)^{-1}[0:mint,0:mint]
+int inverse_interior(gpp_handle* h, GramSlot& s);
+// y = L^{-1} b (forward) / y = L^{-T} b (backward), vectors, in place in x
+int trsv_lower(gpp_handle* h, const double* L, long ld, int n, double* x, bool transposed);
+
+// ---- gram.cu ---------------------------------------------------------------
+int gram_assemble(gpp_handle* h, GramSlot& s);
+int gram_predict(gpp_handle* h, GramSlot& s, const double* d_xtest, int ntest, const double* d_w, double* d_out);
+int gram_theta_test(gpp_handle* h, GramSlot& s, const double* d_xtest, int ntest, double* d_out, long ldo);
+
+// ---- gn.cu -----------------------------------------------------------------
+int gn_eval_F(gpp_handle* h, const double* d_z, bool with_coef);
+int gn_loss(gpp_handle* h, const double* d_z, double* loss_host);
+int gn_step(gpp_handle* h, double step, double* loss_host);
+int gram_kernel_eval(gpp_handle* h, int kernel, const double* kparams, int opx, int opy, const double* d_in, long n,
+                     double* d_out);
