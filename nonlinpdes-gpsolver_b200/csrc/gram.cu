@@ -85,71 +85,140 @@ __host__ __device__ constexpr int lay_op(int lay, int p) {
        :                       (p == 0 ? OP_D1 : p == 1 ? OP_D2 : OP_ID);
 }
 
-constexpr int TI = 64, TJ = 64;   // pair tile: 64 rows x 64 cols; 8 warps, each warp one row at a time, lane -> 2 cols
+// ---------------------------------------------------------------------------------------------------
+// Assembly kernel.  One CTA per lower tile pair (I >= J) of 64 x 64 collocation points, 8 warps.
+//   phase A (row-wise): lane -> columns j = j0 + 2*lane, +1; warp w -> rows i = i0 + w + 8*rr.  One exp per
+//     point pair; every block (p >= q) the pair feeds is written from registers with 128-bit stores
+//     (a warp writes 512 contiguous bytes of one row of Theta).  u1, u2, kappa are stashed in shared memory.
+//   phase B (only I > J): the mirrored entries Theta[(p, j), (q, i)], p > q, of the same unordered pairs are
+//     produced from the stash with d -> -d (no second exp) and written transposed, again 128-bit coalesced.
+// Diagonal tiles (I == J) visit all ordered pairs in phase A and need no phase B.
+// ---------------------------------------------------------------------------------------------------
+constexpr int TP = 64;            // points per tile side
+constexpr int SPAD = TP + 1;      // stash row stride (doubles)
+constexpr int ASM_SMEM = (3 * TP * SPAD + 4 * TP) * 8;
 
-template <int LAYOUT, int P, int Q>
-__device__ __forceinline__ void emit_block(const AsmParams& a, int i, int j, const double* h1, const double* h2,
-                                           const double* h1b, const double* h2b, double kap0, double kap1, bool v1) {
-  // entry (row block P, point i ; col block Q, points j and j+1)
-  if (i >= a.size[P] || j >= a.size[Q]) return;
-  if (P == Q && j > i) return;
-  constexpr int OPX = lay_op(LAYOUT, P), OPY = lay_op(LAYOUT, Q);
-  const double e0 = prefactor<OPX, OPY>(h1, h2) * kap0;
-  double* dst = a.T + (long)(a.off[P] + i) * a.ld + a.off[Q] + j;
-  bool two = v1 && (j + 1 < a.size[Q]) && !(P == Q && j + 1 > i);
-  if (two) {
-    const double e1 = prefactor<OPX, OPY>(h1b, h2b) * kap1;
-    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-      *reinterpret_cast<double2*>(dst) = make_double2(e0, e1);
-    } else {
-      dst[0] = e0; dst[1] = e1;
-    }
+__device__ __forceinline__ void store_pair(double* dst, double e0, double e1, bool ok0, bool ok1, bool vec) {
+  if (ok0 && ok1 && vec) {
+    *reinterpret_cast<double2*>(dst) = make_double2(e0, e1);
   } else {
-    dst[0] = e0;
+    if (ok0) dst[0] = e0;
+    if (ok1) dst[1] = e1;
   }
 }
 
-template <int LAYOUT, int P, int Q>
+// rows: point r (global index) in block P; cols: points c, c+1 in block Q
+template <int LAYOUT, int P, int Q, bool FULL, bool DIAGMASK>
+__device__ __forceinline__ void emit_block(const AsmParams& a, int r, int c, const double* h1, const double* h2,
+                                           const double* h1b, const double* h2b, double kap0, double kap1) {
+  bool ok0 = true, ok1 = true;
+  if (!FULL) {
+    if (r >= a.size[P]) return;
+    ok0 = c < a.size[Q];
+    ok1 = c + 1 < a.size[Q];
+  }
+  if (DIAGMASK && P == Q) { ok0 = ok0 && (c <= r); ok1 = ok1 && (c + 1 <= r); }
+  if (!ok0 && !ok1) return;
+  constexpr int OPX = lay_op(LAYOUT, P), OPY = lay_op(LAYOUT, Q);
+  const double e0 = prefactor<OPX, OPY>(h1, h2) * kap0;
+  const double e1 = prefactor<OPX, OPY>(h1b, h2b) * kap1;
+  double* dst = a.T + (long)(a.off[P] + r) * a.ld + a.off[Q] + c;
+  store_pair(dst, e0, e1, ok0, ok1, ((a.off[Q] | (int)(a.ld & 1)) & 1) == 0);
+}
+
+// MIRROR = false: all blocks p >= q (phase A).  MIRROR = true: only p > q (phase B).
+template <int LAYOUT, int P, int Q, bool FULL, bool DIAGMASK, bool MIRROR>
 struct EmitAll {
-  __device__ static __forceinline__ void run(const AsmParams& a, int i, int j, const double* h1, const double* h2,
-                                             const double* h1b, const double* h2b, double k0, double k1, bool v1) {
-    if (Q <= P) emit_block<LAYOUT, P, Q>(a, i, j, h1, h2, h1b, h2b, k0, k1, v1);
-    if constexpr (Q + 1 < lay_nblk(LAYOUT)) EmitAll<LAYOUT, P, Q + 1>::run(a, i, j, h1, h2, h1b, h2b, k0, k1, v1);
-    else if constexpr (P + 1 < lay_nblk(LAYOUT)) EmitAll<LAYOUT, P + 1, 0>::run(a, i, j, h1, h2, h1b, h2b, k0, k1, v1);
+  __device__ static __forceinline__ void run(const AsmParams& a, int r, int c, const double* h1, const double* h2,
+                                             const double* h1b, const double* h2b, double k0, double k1) {
+    if ((!MIRROR && Q <= P) || (MIRROR && Q < P)) emit_block<LAYOUT, P, Q, FULL, DIAGMASK>(a, r, c, h1, h2, h1b, h2b, k0, k1);
+    if constexpr (Q + 1 < lay_nblk(LAYOUT)) EmitAll<LAYOUT, P, Q + 1, FULL, DIAGMASK, MIRROR>::run(a, r, c, h1, h2, h1b, h2b, k0, k1);
+    else if constexpr (P + 1 < lay_nblk(LAYOUT)) EmitAll<LAYOUT, P + 1, 0, FULL, DIAGMASK, MIRROR>::run(a, r, c, h1, h2, h1b, h2b, k0, k1);
   }
 };
 
-template <int LAYOUT, int KERNEL>
-__global__ void __launch_bounds__(256)
-gram_assemble_kernel(const __grid_constant__ AsmParams a) {
-  __shared__ double sxi[TI][2];
+template <int LAYOUT, int KERNEL, bool FULL, bool DIAG>
+__device__ __forceinline__ void gram_tile(const AsmParams& a, int i0, int j0, double* sm) {
+  double* su1 = sm;                       // [TP][SPAD]
+  double* su2 = sm + TP * SPAD;
+  double* skp = sm + 2 * TP * SPAD;
+  double* sx = sm + 3 * TP * SPAD;        // row points [TP][2], col points [TP][2]
   const int ntot = a.N + a.Nb;
-  const int i0 = blockIdx.y * TI, j0 = blockIdx.x * TJ;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x < TI * 2) {
-    int r = threadIdx.x >> 1, c = threadIdx.x & 1;
-    sxi[r][c] = (i0 + r < ntot) ? a.X[(long)(i0 + r) * 2 + c] : 0.0;
+  {
+    const int r = threadIdx.x >> 1, c = threadIdx.x & 1;   // 256 threads: 64 rows x 2 + 64 cols x 2
+    if (r < TP) sx[r * 2 + c] = (i0 + r < ntot) ? a.X[(long)(i0 + r) * 2 + c] : 0.0;
+    else sx[2 * TP + (r - TP) * 2 + c] = (j0 + (r - TP) < ntot) ? a.X[(long)(j0 + r - TP) * 2 + c] : 0.0;
   }
   __syncthreads();
-  const int j = j0 + 2 * lane;
-  if (j >= ntot) return;
-  const bool v1 = (j + 1 < ntot);
-  const double y1a = a.X[(long)j * 2], y2a = a.X[(long)j * 2 + 1];
-  const double y1b = v1 ? a.X[(long)(j + 1) * 2] : 0.0, y2b = v1 ? a.X[(long)(j + 1) * 2 + 1] : 0.0;
-  for (int rr = warp; rr < TI; rr += 8) {
-    const int i = i0 + rr;
-    if (i >= ntot) break;
-    const double x1 = sxi[rr][0], x2 = sxi[rr][1];
-    double h1[5], h2[5], h1b[5], h2b[5];
-    const double d1 = x1 - y1a, d2 = x2 - y2a;
-    hermite(a.k.b1 * d1, a.k.b1, a.k.c3b1, a.k.c6b1, a.k.c3bb1, h1);
-    hermite(a.k.b2 * d2, a.k.b2, a.k.c3b2, a.k.c6b2, a.k.c3bb2, h2);
-    const double k0 = kappa_of<KERNEL>(a.k, d1, d2);
-    const double d1b = x1 - y1b, d2b = x2 - y2b;
-    hermite(a.k.b1 * d1b, a.k.b1, a.k.c3b1, a.k.c6b1, a.k.c3bb1, h1b);
-    hermite(a.k.b2 * d2b, a.k.b2, a.k.c3b2, a.k.c6b2, a.k.c3bb2, h2b);
-    const double k1 = kappa_of<KERNEL>(a.k, d1b, d2b);
-    EmitAll<LAYOUT, 0, 0>::run(a, i, j, h1, h2, h1b, h2b, k0, k1, v1);
+  // ---- phase A
+  {
+    const int jl = 2 * lane;
+    const double y1a = sx[2 * TP + jl * 2], y2a = sx[2 * TP + jl * 2 + 1];
+    const double y1b = sx[2 * TP + jl * 2 + 2], y2b = sx[2 * TP + jl * 2 + 3];
+#pragma unroll 2
+    for (int rr = 0; rr < TP / 8; ++rr) {
+      const int il = warp + 8 * rr;
+      const int i = i0 + il, j = j0 + jl;
+      if (!FULL && (i >= ntot || j >= ntot)) continue;
+      const double x1 = sx[il * 2], x2 = sx[il * 2 + 1];
+      double h1[5], h2[5], h1b[5], h2b[5];
+      const double d1 = x1 - y1a, d2 = x2 - y2a;
+      const double u1 = a.k.b1 * d1, u2 = a.k.b2 * d2;
+      hermite(u1, a.k.b1, a.k.c3b1, a.k.c6b1, a.k.c3bb1, h1);
+      hermite(u2, a.k.b2, a.k.c3b2, a.k.c6b2, a.k.c3bb2, h2);
+      const double k0 = kappa_of<KERNEL>(a.k, d1, d2);
+      const double d1b = x1 - y1b, d2b = x2 - y2b;
+      const double u1b = a.k.b1 * d1b, u2b = a.k.b2 * d2b;
+      hermite(u1b, a.k.b1, a.k.c3b1, a.k.c6b1, a.k.c3bb1, h1b);
+      hermite(u2b, a.k.b2, a.k.c3b2, a.k.c6b2, a.k.c3bb2, h2b);
+      const double k1 = kappa_of<KERNEL>(a.k, d1b, d2b);
+      EmitAll<LAYOUT, 0, 0, FULL, DIAG, false>::run(a, i, j, h1, h2, h1b, h2b, k0, k1);
+      if (!DIAG) {
+        su1[il * SPAD + jl] = u1; su1[il * SPAD + jl + 1] = u1b;
+        su2[il * SPAD + jl] = u2; su2[il * SPAD + jl + 1] = u2b;
+        skp[il * SPAD + jl] = k0; skp[il * SPAD + jl + 1] = k1;
+      }
+    }
+  }
+  if (DIAG) return;
+  __syncthreads();
+  // ---- phase B: rows = column points j, cols = row points i (two per lane), d -> -d
+  {
+    const int il = 2 * lane;
+#pragma unroll 2
+    for (int rr = 0; rr < TP / 8; ++rr) {
+      const int jl = warp + 8 * rr;
+      const int i = i0 + il, j = j0 + jl;
+      if (!FULL && (i >= ntot || j >= ntot)) continue;
+      double h1[5], h2[5], h1b[5], h2b[5];
+      hermite(-su1[il * SPAD + jl], a.k.b1, a.k.c3b1, a.k.c6b1, a.k.c3bb1, h1);
+      hermite(-su2[il * SPAD + jl], a.k.b2, a.k.c3b2, a.k.c6b2, a.k.c3bb2, h2);
+      hermite(-su1[(il + 1) * SPAD + jl], a.k.b1, a.k.c3b1, a.k.c6b1, a.k.c3bb1, h1b);
+      hermite(-su2[(il + 1) * SPAD + jl], a.k.b2, a.k.c3b2, a.k.c6b2, a.k.c3bb2, h2b);
+      EmitAll<LAYOUT, 0, 0, FULL, false, true>::run(a, j, i, h1, h2, h1b, h2b, skp[il * SPAD + jl], skp[(il + 1) * SPAD + jl]);
+    }
+  }
+}
+
+template <int LAYOUT, int KERNEL>
+__global__ void __launch_bounds__(256, 2)
+gram_assemble_kernel(const __grid_constant__ AsmParams a) {
+  extern __shared__ double asm_smem[];
+  // lower-triangular tile enumeration: blockIdx.x -> (I, J), J <= I
+  const long t = blockIdx.x;
+  int I = static_cast<int>((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+  while ((long)(I + 1) * (I + 2) / 2 <= t) ++I;
+  while ((long)I * (I + 1) / 2 > t) --I;
+  const int J = static_cast<int>(t - (long)I * (I + 1) / 2);
+  const int i0 = I * TP, j0 = J * TP;
+  const bool full = (i0 + TP <= a.N) && (j0 + TP <= a.N);   // all 64 x 64 points interior: every block is valid
+  if (I == J) {
+    if (full) gram_tile<LAYOUT, KERNEL, true, true>(a, i0, j0, asm_smem);
+    else gram_tile<LAYOUT, KERNEL, false, true>(a, i0, j0, asm_smem);
+  } else {
+    if (full) gram_tile<LAYOUT, KERNEL, true, false>(a, i0, j0, asm_smem);
+    else gram_tile<LAYOUT, KERNEL, false, false>(a, i0, j0, asm_smem);
   }
 }
 
@@ -237,9 +306,15 @@ PredParams make_pred(gpp_handle* h, GramSlot& s) {
 template <int LAYOUT>
 int launch_asm(gpp_handle* h, GramSlot& s, const AsmParams& a) {
   const int ntot = s.N + s.Nb;
-  dim3 grid((ntot + TJ - 1) / TJ, (ntot + TI - 1) / TI);
-  if (s.kernel_id == 0) gram_assemble_kernel<LAYOUT, 0><<<grid, 256, 0, h->stream>>>(a);
-  else gram_assemble_kernel<LAYOUT, 1><<<grid, 256, 0, h->stream>>>(a);
+  const long nt = (ntot + TP - 1) / TP;
+  const unsigned grid = (unsigned)(nt * (nt + 1) / 2);
+  if (s.kernel_id == 0) {
+    CUDA_TRY(h, cudaFuncSetAttribute(gram_assemble_kernel<LAYOUT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ASM_SMEM));
+    gram_assemble_kernel<LAYOUT, 0><<<grid, 256, ASM_SMEM, h->stream>>>(a);
+  } else {
+    CUDA_TRY(h, cudaFuncSetAttribute(gram_assemble_kernel<LAYOUT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ASM_SMEM));
+    gram_assemble_kernel<LAYOUT, 1><<<grid, 256, ASM_SMEM, h->stream>>>(a);
+  }
   h->launches++;
   CUDA_TRY(h, cudaGetLastError());
   return GPP_OK;
