@@ -19,37 +19,32 @@ constexpr int LDS_PAD = BASE + 1;
 // A non-positive / NaN pivot is recorded once in *info (1-based global index);
 // sqrt then produces NaN which propagates, like jnp.linalg.cholesky's NaN output.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(BASE)
 potrf_base_kernel(double* __restrict__ A, long ld, int n, int gidx0, int* info) {
   __shared__ double s[BASE * LDS_PAD];
-  const int tid = threadIdx.x;
-  for (int e = tid; e < n * n; e += blockDim.x) {
-    int i = e / n, j = e % n;
-    if (j <= i) s[i * LDS_PAD + j] = A[(long)i * ld + j];
-  }
+  const int i = threadIdx.x;          // one thread per row
+  for (int r = 0; r < n; ++r)         // coalesced row loads
+    if (i <= r) s[r * LDS_PAD + i] = A[(long)r * ld + i];
   __syncthreads();
   for (int j = 0; j < n; ++j) {
-    if (tid == 0) {
-      double d = s[j * LDS_PAD + j];
-      if (!(d > 0.0)) atomicCAS(info, 0, gidx0 + j + 1);
-      s[j * LDS_PAD + j] = sqrt(d);
+    // left-looking, progressive: acc starts at a_ij and is reduced term by term in column order
+    double acc = 0.0;
+    if (i >= j && i < n) {
+      acc = s[i * LDS_PAD + j];
+      const double* ri = s + i * LDS_PAD;
+      const double* rj = s + j * LDS_PAD;
+      for (int k = 0; k < j; ++k) acc = fma(-ri[k], rj[k], acc);
+      if (i == j) {
+        if (!(acc > 0.0)) atomicCAS(info, 0, gidx0 + j + 1);
+        s[j * LDS_PAD + j] = sqrt(acc);
+      }
     }
     __syncthreads();
-    const double djj = s[j * LDS_PAD + j];
-    for (int i = j + 1 + tid; i < n; i += blockDim.x) s[i * LDS_PAD + j] = s[i * LDS_PAD + j] / djj;
-    __syncthreads();
-    // trailing rank-1 update of the lower triangle
-    const int rem = n - j - 1;
-    for (int e = tid; e < rem * rem; e += blockDim.x) {
-      int i = j + 1 + e / rem, k = j + 1 + e % rem;
-      if (k <= i) s[i * LDS_PAD + k] = fma(-s[i * LDS_PAD + j], s[k * LDS_PAD + j], s[i * LDS_PAD + k]);
-    }
+    if (i > j && i < n) s[i * LDS_PAD + j] = acc / s[j * LDS_PAD + j];
     __syncthreads();
   }
-  for (int e = tid; e < n * n; e += blockDim.x) {
-    int i = e / n, j = e % n;
-    if (j <= i) A[(long)i * ld + j] = s[i * LDS_PAD + j];
-  }
+  for (int r = 0; r < n; ++r)
+    if (i <= r) A[(long)r * ld + i] = s[r * LDS_PAD + i];
 }
 
 // ---------------------------------------------------------------------------
@@ -119,30 +114,33 @@ __global__ void symmetrize_kernel(double* __restrict__ A, long ld, int n) {
 // vector triangular solves, 64-wide blocks
 // ---------------------------------------------------------------------------
 // solve the diagonal block in place: forward (L x = b) or backward (L^T x = b)
-__global__ void __launch_bounds__(BASE)
+__global__ void __launch_bounds__(256)
 trsv_diag_kernel(const double* __restrict__ L, long ld, int nb, double* __restrict__ x, int transposed) {
   __shared__ double s[BASE * LDS_PAD];
   __shared__ double xs[BASE];
   const int tid = threadIdx.x;
-  for (int e = tid; e < nb * nb; e += blockDim.x) {
-    int i = e / nb, j = e % nb;
-    if (j <= i) s[i * LDS_PAD + j] = L[(long)i * ld + j];
+  {
+    const int c = tid & 63;
+    for (int r = tid >> 6; r < nb; r += 4)     // 4 rows per pass, coalesced
+      if (c <= r) s[r * LDS_PAD + c] = L[(long)r * ld + c];
   }
   if (tid < nb) xs[tid] = x[tid];
   __syncthreads();
+  if (tid >= BASE) return;
+  // two warps; column-oriented substitution, x_j published through shared memory
   if (!transposed) {
     for (int j = 0; j < nb; ++j) {
       if (tid == j) xs[j] = xs[j] / s[j * LDS_PAD + j];
-      __syncthreads();
+      asm volatile("bar.sync 1, 64;");
       if (tid > j && tid < nb) xs[tid] = fma(-s[tid * LDS_PAD + j], xs[j], xs[tid]);
-      __syncthreads();
+      asm volatile("bar.sync 1, 64;");
     }
   } else {
     for (int j = nb - 1; j >= 0; --j) {
       if (tid == j) xs[j] = xs[j] / s[j * LDS_PAD + j];
-      __syncthreads();
+      asm volatile("bar.sync 1, 64;");
       if (tid < j) xs[tid] = fma(-s[j * LDS_PAD + tid], xs[j], xs[tid]);
-      __syncthreads();
+      asm volatile("bar.sync 1, 64;");
     }
   }
   if (tid < nb) x[tid] = xs[tid];
@@ -220,7 +218,7 @@ int trsm_right_lt(gpp_handle* h, const Mat& P, int pr0, int pc0, int rows, const
 
 int potrf_diag(gpp_handle* h, const Mat& A, int o, int nb, int gidx0) {
   if (nb <= BASE) {
-    potrf_base_kernel<<<1, 256, 0, h->stream>>>(A.base + (long)o * A.ld + o, A.ld, nb, gidx0, h->d_info);
+    potrf_base_kernel<<<1, BASE, 0, h->stream>>>(A.base + (long)o * A.ld + o, A.ld, nb, gidx0, h->d_info);
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
     return GPP_OK;
@@ -319,7 +317,7 @@ int trsv_lower(gpp_handle* h, const double* L, long ld, int n, double* x, bool t
   if (!transposed) {
     for (int j0 = 0; j0 < n; j0 += BASE) {
       const int nb = (n - j0 < BASE) ? (n - j0) : BASE;
-      trsv_diag_kernel<<<1, BASE, 0, h->stream>>>(L + (long)j0 * ld + j0, ld, nb, x + j0, 0);
+      trsv_diag_kernel<<<1, 256, 0, h->stream>>>(L + (long)j0 * ld + j0, ld, nb, x + j0, 0);
       const int rows = n - j0 - nb;
       if (rows > 0)
         trsv_fwd_update_kernel<<<(rows + 15) / 16, 256, 0, h->stream>>>(L + (long)(j0 + nb) * ld + j0, ld, rows, nb,
@@ -331,7 +329,7 @@ int trsv_lower(gpp_handle* h, const double* L, long ld, int n, double* x, bool t
     for (int b = nblk - 1; b >= 0; --b) {
       const int j0 = b * BASE;
       const int nb = (n - j0 < BASE) ? (n - j0) : BASE;
-      trsv_diag_kernel<<<1, BASE, 0, h->stream>>>(L + (long)j0 * ld + j0, ld, nb, x + j0, 1);
+      trsv_diag_kernel<<<1, 256, 0, h->stream>>>(L + (long)j0 * ld + j0, ld, nb, x + j0, 1);
       if (j0 > 0)
         trsv_bwd_update_kernel<<<(j0 + 255) / 256, 256, 0, h->stream>>>(L + (long)j0 * ld, ld, j0, nb, x + j0, x);
       h->launches += 2;

@@ -16,6 +16,7 @@
 #include "gpp_internal.cuh"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <math_constants.h>
 
@@ -310,6 +311,9 @@ int gn_step(gpp_handle* h, double step, double* loss_host) {
   const int N = h->N;
   set_kind(g);
   int rc;
+  static const bool trace = getenv("GPP_TRACE") != nullptr;
+  auto mark = [&](int k) { if (trace) cudaEventRecord(h->ev[2 + k], h->stream); };
+  mark(0);
   // t = L^{-T} s
   for (int s = 0; s < ns; ++s) {
     GramSlot& sl = h->slot[s];
@@ -317,6 +321,7 @@ int gn_step(gpp_handle* h, double step, double* loss_host) {
     rc = trsv_lower(h, sl.T, sl.ld, sl.M, g.t[s], true);
     if (rc) return rc;
   }
+  mark(1);
   // gradient
   {
     GParams a{};
@@ -357,9 +362,11 @@ int gn_step(gpp_handle* h, double step, double* loss_host) {
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
   }
+  mark(2);
   // delta = H^{-1} g via Cholesky (H is SPD: 2 S^T S + data term)
   rc = potrf_lower(h, g.H, g.ldH, g.n, &g.mapH);
   if (rc) return rc;
+  mark(3);
   rc = trsv_lower(h, g.H, g.ldH, g.n, g.g, false);
   if (rc) return rc;
   rc = trsv_lower(h, g.H, g.ldH, g.n, g.g, true);
@@ -367,5 +374,15 @@ int gn_step(gpp_handle* h, double step, double* loss_host) {
   axpy_kernel<<<(g.n + 255) / 256, 256, 0, h->stream>>>(g.z, g.g, step, g.n);
   h->launches++;
   CUDA_TRY(h, cudaGetLastError());
-  return gn_loss(h, g.z, loss_host);
+  mark(4);
+  rc = gn_loss(h, g.z, loss_host);
+  if (trace && !rc) {
+    mark(5);
+    cudaEventSynchronize(h->ev[7]);
+    float t[5];
+    for (int k = 0; k < 5; ++k) cudaEventElapsedTime(&t[k], h->ev[2 + k], h->ev[3 + k]);
+    fprintf(stderr, "[gpp trace] gn_step: trsv L^T %.2f ms | grad+hess %.2f | potrf(H) %.2f | trsv H x2 + axpy %.2f | F, trsv L, loss %.2f\n",
+            t[0], t[1], t[2], t[3], t[4]);
+  }
+  return rc;
 }
