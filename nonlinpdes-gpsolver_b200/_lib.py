@@ -116,6 +116,9 @@ class Engine:
         nb = os.environ.get("GPP_NB")
         if nb:
             self.set_option("NB", float(nb))
+        la = os.environ.get("GPP_LOOKAHEAD")
+        if la is not None:
+            self.set_option("lookahead", float(la))
 
     def close(self):
         if getattr(self, "_h", None):

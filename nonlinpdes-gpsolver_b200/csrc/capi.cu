@@ -73,6 +73,14 @@ int gpp_create(int device, gpp_handle** out) {
     return GPP_CUDA_ERR + 1;
   }
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return GPP_CUDA_ERR; }
+  h->cur = h->stream;
+  {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);   // hi = greatest priority (numerically lowest)
+    cudaStreamCreateWithPriority(&h->sP, cudaStreamNonBlocking, hi);
+    cudaStreamCreateWithPriority(&h->sG[0], cudaStreamNonBlocking, lo);
+    cudaStreamCreateWithPriority(&h->sG[1], cudaStreamNonBlocking, lo);
+  }
   for (auto& e : h->ev) cudaEventCreate(&e);
   cudaMalloc(&h->d_info, sizeof(int));
   cudaMemset(h->d_info, 0, sizeof(int));
@@ -94,6 +102,9 @@ int gpp_destroy(gpp_handle* h) {
   if (h->work) cudaFree(h->work);
   if (h->d_info) cudaFree(h->d_info);
   for (auto& e : h->ev) cudaEventDestroy(e);
+  for (auto& e : h->evpool) cudaEventDestroy(e);
+  if (h->sP) cudaStreamDestroy(h->sP);
+  for (auto& sg : h->sG) if (sg) cudaStreamDestroy(sg);
   cudaStreamDestroy(h->stream);
   delete h;
   return GPP_OK;
@@ -109,6 +120,7 @@ int gpp_set_option(gpp_handle* h, const char* name, double value) {
     h->NB = nb;
     return GPP_OK;
   }
+  if (!strcmp(name, "lookahead")) { h->lookahead = value != 0.0; return GPP_OK; }
   h->err = std::string("unknown option ") + name;
   return -2;
 }

@@ -179,13 +179,9 @@ trsv_bwd_update_kernel(const double* __restrict__ Lrows, long ld, int cols, int 
   x[c] -= acc;
 }
 
-struct Mat {
-  double* base;
-  long ld;
-  const CUtensorMap* map;
-};
+}  // namespace
 
-int trsm_right_lt(gpp_handle* h, const Mat& P, int pr0, int pc0, int rows, const Mat& L, int l0, int nb) {
+int trsm_right_lt(gpp_handle* h, const Mat& P, int pr0, int pc0, int rows, const Mat& L, int lr0, int lc0, int nb) {
   if (rows <= 0 || nb <= 0) return GPP_OK;
   if (nb <= BASE) {
     static bool attr = false;
@@ -194,31 +190,31 @@ int trsm_right_lt(gpp_handle* h, const Mat& P, int pr0, int pc0, int rows, const
       CUDA_TRY(h, cudaFuncSetAttribute(trsm_base_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       attr = true;
     }
-    trsm_base_kernel<<<(rows + TRSM_ROWS - 1) / TRSM_ROWS, TRSM_ROWS, smem, h->stream>>>(
-        P.base + (long)pr0 * P.ld + pc0, P.ld, rows, L.base + (long)l0 * L.ld + l0, L.ld, nb);
+    trsm_base_kernel<<<(rows + TRSM_ROWS - 1) / TRSM_ROWS, TRSM_ROWS, smem, h->cur>>>(
+        P.base + (long)pr0 * P.ld + pc0, P.ld, rows, L.base + (long)lr0 * L.ld + lc0, L.ld, nb);
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
     return GPP_OK;
   }
   const int hh = (int)round_up((nb + 1) / 2, BASE);
-  int rc = trsm_right_lt(h, P, pr0, pc0, rows, L, l0, hh);
+  int rc = trsm_right_lt(h, P, pr0, pc0, rows, L, lr0, lc0, hh);
   if (rc) return rc;
   GemmDesc d{};
   d.mapA = P.map; d.mapB = L.map; d.mapAdiag = nullptr; d.mapBdiag = nullptr;
-  d.a_row0 = pr0; d.b_row0 = l0 + hh;
+  d.a_row0 = pr0; d.b_row0 = lr0 + hh;
   d.C = P.base + (long)pr0 * P.ld + pc0 + hh; d.ldc = P.ld;
   d.Cin = d.C; d.ldcin = P.ld;
   d.m = rows; d.n = nb - hh;
-  d.k0 = pc0; d.k1 = pc0 + hh; d.kb_off = l0 - pc0;
+  d.k0 = pc0; d.k1 = pc0 + hh; d.kb_off = lc0 - pc0;
   d.ktri = 0; d.diag_nb = 0; d.alpha = -1.0; d.lower_only = 0;
   rc = gemm_nt_launch(h, d);
   if (rc) return rc;
-  return trsm_right_lt(h, P, pr0, pc0 + hh, rows, L, l0 + hh, nb - hh);
+  return trsm_right_lt(h, P, pr0, pc0 + hh, rows, L, lr0 + hh, lc0 + hh, nb - hh);
 }
 
 int potrf_diag(gpp_handle* h, const Mat& A, int o, int nb, int gidx0) {
   if (nb <= BASE) {
-    potrf_base_kernel<<<1, BASE, 0, h->stream>>>(A.base + (long)o * A.ld + o, A.ld, nb, gidx0, h->d_info);
+    potrf_base_kernel<<<1, BASE, 0, h->cur>>>(A.base + (long)o * A.ld + o, A.ld, nb, gidx0, h->d_info);
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
     return GPP_OK;
@@ -226,7 +222,7 @@ int potrf_diag(gpp_handle* h, const Mat& A, int o, int nb, int gidx0) {
   const int hh = (int)round_up((nb + 1) / 2, BASE);
   int rc = potrf_diag(h, A, o, hh, gidx0);
   if (rc) return rc;
-  rc = trsm_right_lt(h, A, o + hh, o, nb - hh, A, o, hh);
+  rc = trsm_right_lt(h, A, o + hh, o, nb - hh, A, o, o, hh);
   if (rc) return rc;
   GemmDesc d{};
   d.mapA = A.map; d.mapB = A.map;
@@ -239,31 +235,88 @@ int potrf_diag(gpp_handle* h, const Mat& A, int o, int nb, int gidx0) {
   return potrf_diag(h, A, o + hh, nb - hh, gidx0 + hh);
 }
 
-}  // namespace
+// Left-looking blocked Cholesky: block column j first receives all earlier updates in long-K GEMMs
+// (accumulators stay in registers), then its diagonal block is factorised and the rows below are solved
+// against it.
+//
+// Look-ahead schedule (h->lookahead): the update of column j is split at its last block of K,
+//   G1(j): K = [0, (j-1) NB)   needs columns <= j-2   -> streams sG[j & 1]
+//   G2(j): K = [(j-1) NB, j NB) needs column j-1       -> high-priority stream sP, followed by Panel(j)
+// so that G1(j+1) runs while G2(j) and the latency-bound panel chain of column j are in flight, and fills the
+// SMs left idle by the last wave of G1(j).  K is still consumed in ascending order (progressive accumulation).
+static cudaEvent_t next_event(gpp_handle* h, size_t& used) {
+  if (used == h->evpool.size()) {
+    cudaEvent_t e;
+    cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    h->evpool.push_back(e);
+  }
+  return h->evpool[used++];
+}
 
-// Left-looking blocked Cholesky: block column j first receives all earlier updates in one
-// long-K GEMM (accumulators stay in registers, the block column is read and written once),
-// then its diagonal block is factorised and the rows below are solved against it.
 int potrf_lower(gpp_handle* h, double* A, long ld, int n, const CUtensorMap* map) {
   Mat M{A, ld, map};
   const int NB = h->NB;
+  const int nblk = (n + NB - 1) / NB;
   CUDA_TRY(h, cudaMemsetAsync(h->d_info, 0, sizeof(int), h->stream));
-  for (int j0 = 0; j0 < n; j0 += NB) {
-    const int nbj = (n - j0 < NB) ? (n - j0) : NB;
-    if (j0 > 0) {
-      GemmDesc d{};
-      d.mapA = map; d.mapB = map;
-      d.a_row0 = j0; d.b_row0 = j0;
-      d.C = A + (long)j0 * ld + j0; d.ldc = ld; d.Cin = d.C; d.ldcin = ld;
-      d.m = n - j0; d.n = nbj; d.k0 = 0; d.k1 = j0; d.kb_off = 0;
-      d.alpha = -1.0; d.lower_only = 0;
-      int rc = gemm_nt_launch(h, d);
-      if (rc) return rc;
-    }
+  auto update = [&](int j0, int nbj, int k0, int k1) -> int {
+    if (k1 <= k0) return GPP_OK;
+    GemmDesc d{};
+    d.mapA = map; d.mapB = map;
+    d.a_row0 = j0; d.b_row0 = j0;
+    d.C = A + (long)j0 * ld + j0; d.ldc = ld; d.Cin = d.C; d.ldcin = ld;
+    d.m = n - j0; d.n = nbj; d.k0 = k0; d.k1 = k1; d.kb_off = 0;
+    d.alpha = -1.0; d.lower_only = 0;
+    return gemm_nt_launch(h, d);
+  };
+  auto panel = [&](int j0, int nbj) -> int {
     int rc = potrf_diag(h, M, j0, nbj, j0);
     if (rc) return rc;
-    rc = trsm_right_lt(h, M, j0 + nbj, j0, n - j0 - nbj, M, j0, nbj);
-    if (rc) return rc;
+    return trsm_right_lt(h, M, j0 + nbj, j0, n - j0 - nbj, M, j0, j0, nbj);
+  };
+  const bool la = h->lookahead && nblk >= 4 && h->sP != nullptr;
+  if (!la) {
+    for (int j0 = 0; j0 < n; j0 += NB) {
+      const int nbj = (n - j0 < NB) ? (n - j0) : NB;
+      int rc = update(j0, nbj, 0, j0);
+      if (rc) return rc;
+      rc = panel(j0, nbj);
+      if (rc) return rc;
+    }
+    return GPP_OK;
+  }
+  size_t used = 0;
+  cudaEvent_t ev_start = next_event(h, used);
+  CUDA_TRY(h, cudaEventRecord(ev_start, h->stream));
+  for (int k = 0; k < 2; ++k) CUDA_TRY(h, cudaStreamWaitEvent(h->sG[k], ev_start, 0));
+  CUDA_TRY(h, cudaStreamWaitEvent(h->sP, ev_start, 0));
+  std::vector<cudaEvent_t> evP(nblk);
+  int rc = GPP_OK;
+  for (int j = 0; j < nblk && !rc; ++j) {
+    const int j0 = j * NB;
+    const int nbj = (n - j0 < NB) ? (n - j0) : NB;
+    if (j >= 2) {
+      cudaStream_t sg = h->sG[j & 1];
+      CUDA_TRY(h, cudaStreamWaitEvent(sg, evP[j - 2], 0));
+      h->cur = sg;
+      rc = update(j0, nbj, 0, j0 - NB);
+      if (rc) break;
+      cudaEvent_t eg = next_event(h, used);
+      CUDA_TRY(h, cudaEventRecord(eg, sg));
+      CUDA_TRY(h, cudaStreamWaitEvent(h->sP, eg, 0));
+    }
+    h->cur = h->sP;
+    if (j >= 1) rc = update(j0, nbj, j0 - NB, j0);
+    if (!rc) rc = panel(j0, nbj);
+    evP[j] = next_event(h, used);
+    CUDA_TRY(h, cudaEventRecord(evP[j], h->sP));
+  }
+  h->cur = h->stream;
+  if (rc) return rc;
+  CUDA_TRY(h, cudaStreamWaitEvent(h->stream, evP[nblk - 1], 0));
+  for (int k = 0; k < 2; ++k) {   // the G streams end before the last panel, but keep the main stream ordered after them
+    cudaEvent_t e = next_event(h, used);
+    CUDA_TRY(h, cudaEventRecord(e, h->sG[k]));
+    CUDA_TRY(h, cudaStreamWaitEvent(h->stream, e, 0));
   }
   return GPP_OK;
 }
@@ -278,10 +331,10 @@ int inverse_interior(gpp_handle* h, GramSlot& s) {
     const int nbi = (M - o < NB) ? (M - o) : NB;
     {
       long tot = (long)NB * NB;
-      fill_identity_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(s.udiag + (long)o * NB, NB, NB, NB);
+      fill_identity_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->cur>>>(s.udiag + (long)o * NB, NB, NB, NB);
       h->launches++;
     }
-    int rc = trsm_right_lt(h, UD, o, 0, nbi, T, o, nbi);   // X L_ii^T = I
+    int rc = trsm_right_lt(h, UD, o, 0, nbi, T, o, o, nbi);   // X L_ii^T = I
     if (rc) return rc;
     if (o > 0) {
       GemmDesc d{};
@@ -292,7 +345,7 @@ int inverse_interior(gpp_handle* h, GramSlot& s) {
       d.ktri = 1; d.diag_nb = NB; d.alpha = -1.0; d.lower_only = 0;
       rc = gemm_nt_launch(h, d);
       if (rc) return rc;
-      rc = trsm_right_lt(h, T, 0, o, o, T, o, nbi);
+      rc = trsm_right_lt(h, T, 0, o, o, T, o, o, nbi);
       if (rc) return rc;
     }
   }
@@ -306,7 +359,7 @@ int inverse_interior(gpp_handle* h, GramSlot& s) {
     int rc = gemm_nt_launch(h, d);
     if (rc) return rc;
     dim3 grid((s.Mint + 31) / 32, (s.Mint + 31) / 32), blk(32, 8);
-    symmetrize_kernel<<<grid, blk, 0, h->stream>>>(s.Ainv, s.ldA, s.Mint);
+    symmetrize_kernel<<<grid, blk, 0, h->cur>>>(s.Ainv, s.ldA, s.Mint);
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
   }
@@ -317,10 +370,10 @@ int trsv_lower(gpp_handle* h, const double* L, long ld, int n, double* x, bool t
   if (!transposed) {
     for (int j0 = 0; j0 < n; j0 += BASE) {
       const int nb = (n - j0 < BASE) ? (n - j0) : BASE;
-      trsv_diag_kernel<<<1, 256, 0, h->stream>>>(L + (long)j0 * ld + j0, ld, nb, x + j0, 0);
+      trsv_diag_kernel<<<1, 256, 0, h->cur>>>(L + (long)j0 * ld + j0, ld, nb, x + j0, 0);
       const int rows = n - j0 - nb;
       if (rows > 0)
-        trsv_fwd_update_kernel<<<(rows + 15) / 16, 256, 0, h->stream>>>(L + (long)(j0 + nb) * ld + j0, ld, rows, nb,
+        trsv_fwd_update_kernel<<<(rows + 15) / 16, 256, 0, h->cur>>>(L + (long)(j0 + nb) * ld + j0, ld, rows, nb,
                                                                          x + j0, x + j0 + nb);
       h->launches += 2;
     }
@@ -329,9 +382,9 @@ int trsv_lower(gpp_handle* h, const double* L, long ld, int n, double* x, bool t
     for (int b = nblk - 1; b >= 0; --b) {
       const int j0 = b * BASE;
       const int nb = (n - j0 < BASE) ? (n - j0) : BASE;
-      trsv_diag_kernel<<<1, 256, 0, h->stream>>>(L + (long)j0 * ld + j0, ld, nb, x + j0, 1);
+      trsv_diag_kernel<<<1, 256, 0, h->cur>>>(L + (long)j0 * ld + j0, ld, nb, x + j0, 1);
       if (j0 > 0)
-        trsv_bwd_update_kernel<<<(j0 + 255) / 256, 256, 0, h->stream>>>(L + (long)j0 * ld, ld, j0, nb, x + j0, x);
+        trsv_bwd_update_kernel<<<(j0 + 255) / 256, 256, 0, h->cur>>>(L + (long)j0 * ld, ld, j0, nb, x + j0, x);
       h->launches += 2;
     }
   }

@@ -279,7 +279,7 @@ int gemm_nt_launch(gpp_handle* h, const GemmDesc& d) {
   } else {
     ntiles = (long)p.tiles_m * p.tiles_n;
   }
-  gemm_nt_dmma_kernel<<<(unsigned)ntiles, THREADS, SMEM_BYTES, h->stream>>>(p);
+  gemm_nt_dmma_kernel<<<(unsigned)ntiles, THREADS, SMEM_BYTES, h->cur>>>(p);
   h->launches++;
   CUDA_TRY(h, cudaGetLastError());
   return GPP_OK;

@@ -85,7 +85,12 @@ struct GnState {
 
 struct gpp_handle {
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;      // main stream (all public calls are ordered on it)
+  cudaStream_t cur = nullptr;         // stream the launch helpers use right now (= stream unless look-ahead is active)
+  cudaStream_t sG[2] = {nullptr, nullptr};  // look-ahead: alternating streams of the long-K updates
+  cudaStream_t sP = nullptr;          // look-ahead: high-priority stream of the panel chain
+  std::vector<cudaEvent_t> evpool;    // events of the look-ahead dependency graph
+  int lookahead = 1;
   std::string err;
   int N = 0, Nb = 0;
   double* Xd = nullptr;       // N x 2
@@ -140,6 +145,15 @@ int gemm_nt_launch(gpp_handle* h, const GemmDesc& d);
 int make_tensor_map(gpp_handle* h, CUtensorMap* map, const double* base, long rows, long cols, long ld);
 
 // ---- chol.cu ---------------------------------------------------------------
+struct Mat {
+  double* base;
+  long ld;
+  const CUtensorMap* map;
+};
+// X * L^T = P in place; P = rows x nb block of P at (pr0, pc0); L = nb x nb lower block of L at (lr0, lc0)
+int trsm_right_lt(gpp_handle* h, const Mat& P, int pr0, int pc0, int rows, const Mat& L, int lr0, int lc0, int nb);
+// Cholesky of the nb x nb diagonal block at (o, o) of A (recursive, 64-wide base), gidx0 = global pivot offset
+int potrf_diag(gpp_handle* h, const Mat& A, int o, int nb, int gidx0);
 // Blocked lower Cholesky of the n x n matrix at A (row-major, ld), in place, using map for TMA.
 int potrf_lower(gpp_handle* h, double* A, long ld, int n, const CUtensorMap* map);
 // U = L^{-T} into the strict upper triangle + udiag, then Ainv = (L L^T)^{-1}[0:mint,0:mint]
