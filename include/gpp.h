@@ -98,6 +98,23 @@ int gpp_theta_test(gpp_handle* h, int slot, const double* X_test, int N_test, do
 int gpp_kernel_eval(gpp_handle* h, int kernel, const double* kparams, int op_x, int op_y, const double* x1,
                     const double* x2, const double* y1, const double* y2, long n, double* out);
 
+/* ---- multi-GPU: one process per GPU, block rows of Theta dealt cyclically (P x 1 block-cyclic), NCCL over NVLink.
+ * New functionality (the reference is single-process).  Rank 0 creates the 128-byte NCCL id and
+ * distributes it out of band (torch.distributed / MPI / a file); every rank then calls gpp_dist_init. */
+int gpp_dist_unique_id(unsigned char* id128);
+int gpp_dist_init(gpp_handle* h, int rank, int world, const unsigned char* id128);
+int gpp_dist_finalize(gpp_handle* h);
+/* row-sharded Gram_matrix_assembly: this rank's block rows (NB rows each, block b on rank b % world), no exchange */
+int gpp_dist_gram_assemble(gpp_handle* h, int layout, int kernel, const double* kparams);
+int gpp_dist_local_rows(gpp_handle* h, int* n_local_rows, int* M);
+/* nugget support: full diagonal on every rank (all-reduce) / add a full-length vector to the owned diagonal entries */
+int gpp_dist_get_diag(gpp_handle* h, double* diag_out);
+int gpp_dist_add_diag(gpp_handle* h, const double* add);
+/* distributed Gram_Cholesky: per block column one ncclBroadcast of the factored block row, then local DMMA updates */
+int gpp_dist_potrf(gpp_handle* h, int* info);
+/* this rank's rows (n_local_rows x M, dense, zeros above the diagonal): tests / gathering L */
+int gpp_dist_download_local(gpp_handle* h, double* out);
+
 #ifdef __cplusplus
 }
 #endif

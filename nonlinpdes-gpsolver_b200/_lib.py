@@ -53,6 +53,15 @@ def _sig(lib):
         "gpp_predict": [H, C.c_int, _dp, C.c_int, _dp, _dp],
         "gpp_theta_test": [H, C.c_int, _dp, C.c_int, _dp],
         "gpp_kernel_eval": [H, C.c_int, _dp, C.c_int, C.c_int, _dp, _dp, _dp, _dp, C.c_long, _dp],
+        "gpp_dist_unique_id": [C.POINTER(C.c_ubyte)],
+        "gpp_dist_init": [H, C.c_int, C.c_int, C.POINTER(C.c_ubyte)],
+        "gpp_dist_finalize": [H],
+        "gpp_dist_gram_assemble": [H, C.c_int, C.c_int, _dp],
+        "gpp_dist_local_rows": [H, _ip, _ip],
+        "gpp_dist_get_diag": [H, _dp],
+        "gpp_dist_add_diag": [H, _dp],
+        "gpp_dist_potrf": [H, _ip],
+        "gpp_dist_download_local": [H, _dp],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)
@@ -280,6 +289,55 @@ class Engine:
         self._ck(self._lib.gpp_kernel_eval(self._h, KERNEL[kernel], _ptr(kp), op_x, op_y, _ptr(flat[0]), _ptr(flat[1]),
                                            _ptr(flat[2]), _ptr(flat[3]), out.shape[0], _ptr(out)), "gpp_kernel_eval")
         return out.reshape(shape)
+
+
+    # ---- multi-GPU (one process per GPU); see _dist.py for the torch.distributed plumbing
+    def dist_init(self, rank, world, id_bytes):
+        buf = (C.c_ubyte * 128).from_buffer_copy(bytes(id_bytes))
+        self._ck(self._lib.gpp_dist_init(self._h, int(rank), int(world), buf), "gpp_dist_init")
+        self.rank, self.world = int(rank), int(world)
+
+    def dist_finalize(self):
+        self._ck(self._lib.gpp_dist_finalize(self._h), "gpp_dist_finalize")
+
+    def dist_gram_assemble(self, layout, kernel, kernel_parameter):
+        kp = kernel_params(kernel, kernel_parameter)
+        self._ck(self._lib.gpp_dist_gram_assemble(self._h, LAYOUT[layout], KERNEL[kernel], _ptr(kp)), "gpp_dist_gram_assemble")
+
+    def dist_local_rows(self):
+        n, M = C.c_int(), C.c_int()
+        self._ck(self._lib.gpp_dist_local_rows(self._h, C.byref(n), C.byref(M)), "gpp_dist_local_rows")
+        return n.value, M.value
+
+    def dist_get_diag(self):
+        _, M = self.dist_local_rows()
+        out = np.empty(M)
+        self._ck(self._lib.gpp_dist_get_diag(self._h, _ptr(out)), "gpp_dist_get_diag")
+        return out
+
+    def dist_add_diag(self, add):
+        _, M = self.dist_local_rows()
+        add = _f64(add, (M,))
+        self._ck(self._lib.gpp_dist_add_diag(self._h, _ptr(add)), "gpp_dist_add_diag")
+
+    def dist_potrf(self):
+        info = C.c_int()
+        self._ck(self._lib.gpp_dist_potrf(self._h, C.byref(info)), "gpp_dist_potrf")
+        return info.value
+
+    def dist_download_local(self):
+        n, M = self.dist_local_rows()
+        out = np.empty((n, M))
+        self._ck(self._lib.gpp_dist_download_local(self._h, _ptr(out)), "gpp_dist_download_local")
+        return out
+
+
+def nccl_unique_id():
+    lib = load()
+    buf = (C.c_ubyte * 128)()
+    if lib.gpp_dist_unique_id(buf) != 0:
+        raise GppError("gpp_dist_unique_id failed")
+    return bytes(buf)
 
 
 _default_engine = None

@@ -212,27 +212,27 @@ int trsm_right_lt(gpp_handle* h, const Mat& P, int pr0, int pc0, int rows, const
   return trsm_right_lt(h, P, pr0, pc0 + hh, rows, L, lr0 + hh, lc0 + hh, nb - hh);
 }
 
-int potrf_diag(gpp_handle* h, const Mat& A, int o, int nb, int gidx0) {
+int potrf_diag(gpp_handle* h, const Mat& A, int r0, int c0, int nb, int gidx0) {
   if (nb <= BASE) {
-    potrf_base_kernel<<<1, BASE, 0, h->cur>>>(A.base + (long)o * A.ld + o, A.ld, nb, gidx0, h->d_info);
+    potrf_base_kernel<<<1, BASE, 0, h->cur>>>(A.base + (long)r0 * A.ld + c0, A.ld, nb, gidx0, h->d_info);
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
     return GPP_OK;
   }
   const int hh = (int)round_up((nb + 1) / 2, BASE);
-  int rc = potrf_diag(h, A, o, hh, gidx0);
+  int rc = potrf_diag(h, A, r0, c0, hh, gidx0);
   if (rc) return rc;
-  rc = trsm_right_lt(h, A, o + hh, o, nb - hh, A, o, o, hh);
+  rc = trsm_right_lt(h, A, r0 + hh, c0, nb - hh, A, r0, c0, hh);
   if (rc) return rc;
   GemmDesc d{};
   d.mapA = A.map; d.mapB = A.map;
-  d.a_row0 = o + hh; d.b_row0 = o + hh;
-  d.C = A.base + (long)(o + hh) * A.ld + o + hh; d.ldc = A.ld; d.Cin = d.C; d.ldcin = A.ld;
-  d.m = nb - hh; d.n = nb - hh; d.k0 = o; d.k1 = o + hh; d.kb_off = 0;
+  d.a_row0 = r0 + hh; d.b_row0 = r0 + hh;
+  d.C = A.base + (long)(r0 + hh) * A.ld + c0 + hh; d.ldc = A.ld; d.Cin = d.C; d.ldcin = A.ld;
+  d.m = nb - hh; d.n = nb - hh; d.k0 = c0; d.k1 = c0 + hh; d.kb_off = 0;
   d.alpha = -1.0; d.lower_only = 1;
   rc = gemm_nt_launch(h, d);
   if (rc) return rc;
-  return potrf_diag(h, A, o + hh, nb - hh, gidx0 + hh);
+  return potrf_diag(h, A, r0 + hh, c0 + hh, nb - hh, gidx0 + hh);
 }
 
 // Left-looking blocked Cholesky: block column j first receives all earlier updates in long-K GEMMs
@@ -269,7 +269,7 @@ int potrf_lower(gpp_handle* h, double* A, long ld, int n, const CUtensorMap* map
     return gemm_nt_launch(h, d);
   };
   auto panel = [&](int j0, int nbj) -> int {
-    int rc = potrf_diag(h, M, j0, nbj, j0);
+    int rc = potrf_diag(h, M, j0, j0, nbj, j0);
     if (rc) return rc;
     return trsm_right_lt(h, M, j0 + nbj, j0, n - j0 - nbj, M, j0, j0, nbj);
   };

@@ -152,8 +152,10 @@ struct Mat {
 };
 // X * L^T = P in place; P = rows x nb block of P at (pr0, pc0); L = nb x nb lower block of L at (lr0, lc0)
 int trsm_right_lt(gpp_handle* h, const Mat& P, int pr0, int pc0, int rows, const Mat& L, int lr0, int lc0, int nb);
-// Cholesky of the nb x nb diagonal block at (o, o) of A (recursive, 64-wide base), gidx0 = global pivot offset
-int potrf_diag(gpp_handle* h, const Mat& A, int o, int nb, int gidx0);
+// Cholesky of the nb x nb block at (r0, c0) of A (recursive, 64-wide base), gidx0 = global pivot offset
+int potrf_diag(gpp_handle* h, const Mat& A, int r0, int c0, int nb, int gidx0);
+// ---- gram.cu: rows [i_begin, i_begin + nrows) of row-operator block `prow`, all column blocks q <= prow
+int gram_assemble_rows(gpp_handle* h, GramSlot& s, int prow, int i_begin, int nrows, double* dst, long ld);
 // Blocked lower Cholesky of the n x n matrix at A (row-major, ld), in place, using map for TMA.
 int potrf_lower(gpp_handle* h, double* A, long ld, int n, const CUtensorMap* map);
 // U = L^{-T} into the strict upper triangle + udiag, then Ainv = (L L^T)^{-1}[0:mint,0:mint]

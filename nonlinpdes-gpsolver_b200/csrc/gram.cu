@@ -398,3 +398,111 @@ int gram_kernel_eval(gpp_handle* h, int kernel, const double* kparams, int opx, 
   CUDA_TRY(h, cudaGetLastError());
   return GPP_OK;
 }
+
+// ---- row-panel assembly for the row-sharded (multi-GPU) layout ------------------------------------------
+// Rows [i_begin, i_begin + nrows) of row-operator block PROW, every column block q <= PROW (q == PROW: j <= i),
+// written to dst (row 0 of dst = point i_begin).  Ordered pairs: no mirrored writes, so a rank touches only
+// the rows it owns and the assembly needs no exchange.
+namespace {
+struct RowParams {
+  AsmParams a;
+  int i_begin, nrows;
+  double* dst; long ldd;
+};
+
+template <int LAYOUT, int P, int Q>
+struct EmitRow {
+  __device__ static __forceinline__ void run(const RowParams& r, double* drow, int i, int j, const double* h1, const double* h2,
+                                             const double* h1b, const double* h2b, double k0, double k1) {
+    if (Q <= P) {
+      bool ok0 = j < r.a.size[Q], ok1 = j + 1 < r.a.size[Q];
+      if (P == Q) { ok0 = ok0 && (j <= i); ok1 = ok1 && (j + 1 <= i); }
+      if (ok0 || ok1) {
+        constexpr int OPX = lay_op(LAYOUT, P), OPY = lay_op(LAYOUT, Q);
+        const double e0 = prefactor<OPX, OPY>(h1, h2) * k0;
+        const double e1 = prefactor<OPX, OPY>(h1b, h2b) * k1;
+        store_pair(drow + r.a.off[Q] + j, e0, e1, ok0, ok1, ((r.a.off[Q] | (int)(r.ldd & 1)) & 1) == 0);
+      }
+    }
+    if constexpr (Q + 1 <= P) EmitRow<LAYOUT, P, Q + 1>::run(r, drow, i, j, h1, h2, h1b, h2b, k0, k1);
+  }
+};
+
+template <int LAYOUT, int KERNEL, int P>
+__global__ void __launch_bounds__(256)
+gram_rows_kernel(const __grid_constant__ RowParams r) {
+  const AsmParams& a = r.a;
+  const int ntot = a.N + a.Nb;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x * 64 + 2 * lane;
+  if (j >= ntot) return;
+  const bool v1 = j + 1 < ntot;
+  const double y1a = a.X[(long)j * 2], y2a = a.X[(long)j * 2 + 1];
+  const double y1b = v1 ? a.X[(long)(j + 1) * 2] : 0.0, y2b = v1 ? a.X[(long)(j + 1) * 2 + 1] : 0.0;
+  for (int rr = warp; rr < 64; rr += 8) {
+    const int il = blockIdx.y * 64 + rr;
+    if (il >= r.nrows) break;
+    const int i = r.i_begin + il;
+    const double x1 = a.X[(long)i * 2], x2 = a.X[(long)i * 2 + 1];
+    double h1[5], h2[5], h1b[5], h2b[5];
+    const double d1 = x1 - y1a, d2 = x2 - y2a;
+    hermite(a.k.b1 * d1, a.k.b1, a.k.c3b1, a.k.c6b1, a.k.c3bb1, h1);
+    hermite(a.k.b2 * d2, a.k.b2, a.k.c3b2, a.k.c6b2, a.k.c3bb2, h2);
+    const double k0 = kappa_of<KERNEL>(a.k, d1, d2);
+    const double d1b = x1 - y1b, d2b = x2 - y2b;
+    hermite(a.k.b1 * d1b, a.k.b1, a.k.c3b1, a.k.c6b1, a.k.c3bb1, h1b);
+    hermite(a.k.b2 * d2b, a.k.b2, a.k.c3b2, a.k.c6b2, a.k.c3bb2, h2b);
+    const double k1 = v1 ? kappa_of<KERNEL>(a.k, d1b, d2b) : 0.0;
+    EmitRow<LAYOUT, P, 0>::run(r, r.dst + (long)il * r.ldd, i, j, h1, h2, h1b, h2b, k0, k1);
+  }
+}
+
+template <int LAYOUT, int P>
+int launch_rows_p(gpp_handle* h, GramSlot& s, const RowParams& r) {
+  if constexpr (P < lay_nblk(LAYOUT)) {
+    // columns needed: blocks q <= P; the widest is q = P itself (j <= i) or any earlier block (all N points)
+    const int ncol = (P == 0) ? (r.i_begin + r.nrows) : r.a.size[0] > r.a.size[P] ? r.a.size[0] : r.a.size[P];
+    dim3 grid((ncol + 63) / 64, (r.nrows + 63) / 64);
+    if (s.kernel_id == 0) gram_rows_kernel<LAYOUT, 0, P><<<grid, 256, 0, h->cur>>>(r);
+    else gram_rows_kernel<LAYOUT, 1, P><<<grid, 256, 0, h->cur>>>(r);
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    return GPP_OK;
+  } else {
+    h->err = "bad row block";
+    return -1;
+  }
+}
+
+template <int LAYOUT>
+int launch_rows(gpp_handle* h, GramSlot& s, int prow, const RowParams& r) {
+  switch (prow) {
+    case 0: return launch_rows_p<LAYOUT, 0>(h, s, r);
+    case 1: return launch_rows_p<LAYOUT, 1>(h, s, r);
+    case 2: return launch_rows_p<LAYOUT, 2>(h, s, r);
+    case 3: return launch_rows_p<LAYOUT, 3>(h, s, r);
+  }
+  h->err = "bad row block";
+  return -1;
+}
+}  // namespace
+
+int gram_assemble_rows(gpp_handle* h, GramSlot& s, int prow, int i_begin, int nrows, double* dst, long ld) {
+  if (nrows <= 0) return GPP_OK;
+  RowParams r{};
+  r.a.k = make_kparams(s);
+  r.a.X = h->Xall; r.a.N = s.N; r.a.Nb = s.Nb; r.a.T = nullptr; r.a.ld = ld;
+  for (int q = 0; q < s.lay.nblk; ++q) {
+    r.a.off[q] = s.off[q];
+    r.a.size[q] = s.N + (s.lay.with_bdy[q] ? s.Nb : 0);
+  }
+  r.i_begin = i_begin; r.nrows = nrows; r.dst = dst; r.ldd = ld;
+  switch (s.layout_id) {
+    case LAY_ELLIPTIC: return launch_rows<LAY_ELLIPTIC>(h, s, prow, r);
+    case LAY_BURGERS:  return launch_rows<LAY_BURGERS>(h, s, prow, r);
+    case LAY_EIKONAL:  return launch_rows<LAY_EIKONAL>(h, s, prow, r);
+    case LAY_DARCY_A:  return launch_rows<LAY_DARCY_A>(h, s, prow, r);
+  }
+  h->err = "bad layout";
+  return -1;
+}
