@@ -35,6 +35,7 @@ typedef struct gpp_handle gpp_handle;
 #define GPP_PDE_BURGERS 1
 #define GPP_PDE_EIKONAL 2
 #define GPP_PDE_DARCY 3
+#define GPP_PDE_ELLIPTIC_RELAXED 4 /* GN_relaxed_method, src/PDEs.py:137-201: z = [v; w], params {alpha, m, pen_lambda} */
 
 int gpp_create(int device, gpp_handle** out);
 int gpp_destroy(gpp_handle* h);

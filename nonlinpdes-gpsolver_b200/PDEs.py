@@ -213,8 +213,50 @@ class Nonlinear_elliptic2d(_GPProblem):
     def Gram_matrix(self, kernel='Gaussian', kernel_parameter=0.2, nugget=1e-8, nugget_type='adaptive'):
         self._gram(kernel, kernel_parameter, nugget, nugget_type)
 
+    def loss_relaxed(self, z, pen_lambda):
+        eng = self._engine()
+        eng.gn_setup('Nonlinear_elliptic_relaxed', [float(self.alpha), float(self.m), float(pen_lambda)], self.rhs_f, self.bdy_g)
+        eng.gn_set_z(z)
+        return eng.gn_loss()
+
     def GN_relaxed_method(self, max_iter=3, step_size=1, initial_sol='rdm', pen_lambda=1e-10, print_hist=True):
-        raise NotImplementedError("relaxed Gauss-Newton (src/PDEs.py:137-201) is scheduled as a 'next' row (SURVEY 8f-2)")
+        """src/PDEs.py:171-201: unknowns z = [v; w] (2N), penalised constraint -v + alpha w^m = f.
+        H = 2 E^T Theta^{-1} E + (2/lambda) B^T B uses the same interior inverse block as the elimination path."""
+        print(f'Relaxed approach: penalization parameter = {pen_lambda}')
+        eng = self._engine()
+        N = self.N_domain
+        if isinstance(initial_sol, str):
+            if initial_sol != 'rdm':
+                raise ValueError(f"initial_sol {initial_sol!r} not supported")
+            sol = random.normal(0.0, 1.0, (2 * N))
+        else:
+            sol = onp.array(initial_sol, dtype=onp.float64).reshape(2 * N)
+        self.init_sol = sol
+        eng.gn_setup('Nonlinear_elliptic_relaxed', [float(self.alpha), float(self.m), float(pen_lambda)], self.rhs_f, self.bdy_g)
+        eng.timer_start()
+        eng.inverse(0)
+        self.timings['inverse_ms'] = eng.timer_stop()
+        eng.gn_set_z(sol)
+        eng.timer_start()
+        loss_now = eng.gn_loss()
+        loss_hist = [loss_now]
+        if onp.isnan(loss_now):
+            print('[Error] Loss is nan: maybe nugget is too small!')
+        if print_hist:
+            print('iter = 0', 'Loss =', loss_now)
+        for iter_step in range(1, max_iter + 1):
+            loss_now = eng.gn_step(step_size)
+            if onp.isnan(loss_now):
+                print('[Error] Loss is nan: maybe nugget is too small!')
+            loss_hist.append(loss_now)
+            if print_hist:
+                print('iter = ', iter_step, 'Gauss-Newton step size =', step_size, ' Loss = ', loss_now)
+        self.timings['gn_ms'] = eng.timer_stop()
+        self.max_iter, self.step_size, self.loss_hist = max_iter, step_size, loss_hist
+        sol = eng.gn_get_z()
+        self.sol = sol
+        self.sol_vec = onp.append(sol, self.bdy_g)        # :199
+        self.sol_sampled_pts = sol[N:]                    # :201
 
 
 class Burgers(_GPProblem):

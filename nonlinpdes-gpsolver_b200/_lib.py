@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libgpp_b200.so")
 
 LAYOUT = {"Nonlinear_elliptic": 0, "Burgers": 1, "Eikonal": 2, "Darcy_flow2d": 2, "Darcy_flow2d_a": 3}
 KERNEL = {"Gaussian": 0, "anisotropic_Gaussian": 1}
-PDE = {"Nonlinear_elliptic": 0, "Burgers": 1, "Eikonal": 2, "Darcy_flow2d": 3}
+PDE = {"Nonlinear_elliptic": 0, "Burgers": 1, "Eikonal": 2, "Darcy_flow2d": 3, "Nonlinear_elliptic_relaxed": 4}
 
 _lib = None
 _dp = C.POINTER(C.c_double)
@@ -229,7 +229,7 @@ class Engine:
         if data_u is not None:
             data_u = _f64(data_u)
             nd = data_u.shape[0]
-        self.nz = {0: 1, 1: 3, 2: 3, 3: 6}[PDE[pde]]
+        self.nz = {0: 1, 1: 3, 2: 3, 3: 6, 4: 2}[PDE[pde]]
         self._ck(self._lib.gpp_gn_setup(self._h, PDE[pde], _ptr(params), _ptr(rhs_f), _ptr(bdy_g) if self.Nb else None,
                                         _ptr(data_u) if nd else None, nd, float(noise)), "gpp_gn_setup")
 

@@ -324,19 +324,23 @@ int gpp_solve_vec(gpp_handle* h, int slot, const double* b, double* x) {
 int gpp_gn_setup(gpp_handle* h, int pde, const double* params, const double* rhs_f, const double* bdy_g,
                  const double* data_u, int N_data, double noise) {
   if (!h) return -1;
-  if (pde < 0 || pde > 3) { h->err = "bad pde"; return -2; }
+  if (pde < 0 || pde > 4) { h->err = "bad pde"; return -2; }
   if (!rhs_f || (h->Nb > 0 && !bdy_g)) { h->err = "rhs_f / bdy_g missing"; return -4; }
   CUDA_TRY(h, cudaSetDevice(h->device));
   GnState& g = h->gn;
   const int N = h->N, Nb = h->Nb;
   g.pde = pde;
-  g.nz = (pde == PDE_ELLIPTIC) ? 1 : (pde == PDE_DARCY ? 6 : 3);
+  g.nz = (pde == PDE_ELLIPTIC) ? 1 : (pde == PDE_DARCY ? 6 : (pde == PDE_ELLIPTIC_RELAXED ? 2 : 3));
   g.n = g.nz * N;
   memset(g.params, 0, sizeof(g.params));
   g.m_int = 0;
-  if (pde == PDE_ELLIPTIC) {
+  if (pde == PDE_ELLIPTIC || pde == PDE_ELLIPTIC_RELAXED) {
     if (!params) return -3;
     g.params[0] = params[0]; g.params[1] = params[1]; g.params[2] = params[0] * params[1];
+    if (pde == PDE_ELLIPTIC_RELAXED) {
+      if (!(params[2] > 0.0)) { h->err = "pen_lambda must be positive"; return -3; }
+      g.params[3] = params[2];
+    }
     const double m = params[1];
     g.m_int = (m == (double)(int)m && m >= 1.0 && m <= 64.0) ? (int)m : 0;
   } else if (pde == PDE_BURGERS) {
@@ -347,7 +351,7 @@ int gpp_gn_setup(gpp_handle* h, int pde, const double* params, const double* rhs
     g.params[0] = params[0];
   }
   const int need_slots = (pde == PDE_DARCY) ? 2 : 1;
-  const int want_layout[2] = {pde == PDE_ELLIPTIC ? LAY_ELLIPTIC : (pde == PDE_BURGERS ? LAY_BURGERS : LAY_EIKONAL), LAY_DARCY_A};
+  const int want_layout[2] = {(pde == PDE_ELLIPTIC || pde == PDE_ELLIPTIC_RELAXED) ? LAY_ELLIPTIC : (pde == PDE_BURGERS ? LAY_BURGERS : LAY_EIKONAL), LAY_DARCY_A};
   for (int s = 0; s < need_slots; ++s) {
     if (!h->slot[s].T || h->slot[s].layout_id != want_layout[s]) { h->err = "Gram slot missing or wrong layout for this PDE"; return -5; }
   }

@@ -119,6 +119,19 @@ __global__ void fcoef_kernel(const FParams a) {
         cptr(a.coef, N, 0, 2, 2)[i] = (2.0 * v2) / a.p0;
         cptr(a.coef, N, 0, 3, 0)[i] = 1.0;
       }
+    } else if (a.pde == PDE_ELLIPTIC_RELAXED) {
+      // relaxed formulation, z = [v; w]: F = [v; w; g], ss2 = -v + alpha*w^m - f      src/PDEs.py:137-148
+      const double v = a.z[i], w = a.z[N + i];
+      const double wm = (a.m_int >= 1) ? ipow(w, a.m_int) : pow(w, a.p1);
+      a.F0[i] = v;
+      a.F0[N + i] = w;
+      cptr(a.coef, N, 1, 0, 0)[i] = ((-v) + a.p0 * wm) - a.rhs_f[i];                  // ss2
+      if (a.with_coef) {
+        const double wm1 = (a.m_int >= 2) ? ipow(w, a.m_int - 1) : ((a.m_int == 1) ? 1.0 : pow(w, a.p1 - 1.0));
+        cptr(a.coef, N, 1, 0, 1)[i] = a.p2 * wm1;                                      // alpha*m*w^(m-1)   :164
+        cptr(a.coef, N, 0, 0, 0)[i] = 1.0;
+        cptr(a.coef, N, 0, 1, 1)[i] = 1.0;
+      }
     } else {  // PDE_DARCY: z = [w0 w1 w2 v0 v1 v2]; slot 0 = Theta_u, slot 1 = Theta_a
       const double w0 = a.z[i], w1 = a.z[N + i], w2 = a.z[2 * N + i];
       const double v0 = a.z[3 * N + i], v1 = a.z[4 * N + i], v2 = a.z[5 * N + i];
@@ -145,7 +158,7 @@ __global__ void fcoef_kernel(const FParams a) {
     }
   }
   if (i < a.Nb) {
-    const int nb_rows = (a.pde == PDE_ELLIPTIC) ? 2 * N : 4 * N;
+    const int nb_rows = (a.pde == PDE_ELLIPTIC || a.pde == PDE_ELLIPTIC_RELAXED) ? 2 * N : 4 * N;
     a.F0[nb_rows + i] = a.bdy_g[i];
   }
 }
@@ -160,7 +173,7 @@ sumsq_kernel(const double* __restrict__ a, int na, const double* __restrict__ b,
   for (int i = threadIdx.x; i < na; i += 1024) acc += a[i] * a[i];
   for (int i = threadIdx.x; i < nb; i += 1024) acc += b[i] * b[i];
   double mis = 0.0;
-  for (int i = threadIdx.x; i < ndata; i += 1024) { double d = v0[i] - data[i]; mis += d * d; }
+  for (int i = threadIdx.x; i < ndata; i += 1024) { double d = data ? v0[i] - data[i] : v0[i]; mis += d * d; }
   sh[threadIdx.x] = acc + inv_noise2 * mis;
   __syncthreads();
   for (int s = 512; s >= 1; s >>= 1) {
@@ -238,6 +251,20 @@ __global__ void grad_kernel(const __grid_constant__ GParams a) {
   }
 }
 
+// relaxed elliptic: H += (2/lambda) B^T B, g += (2/lambda) B^T ss2 with B = [-I, diag(c)]   src/PDEs.py:166-169
+__global__ void relax_penalty_kernel(int N, double two_over_lam, const double* __restrict__ ss2, const double* __restrict__ c,
+                                     double* __restrict__ H, long ldH, double* __restrict__ g) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const double ci = c[i], si = ss2[i];
+  H[(long)i * ldH + i] += two_over_lam;
+  H[(long)i * ldH + N + i] += -(two_over_lam * ci);
+  H[(long)(N + i) * ldH + i] += -(two_over_lam * ci);
+  H[(long)(N + i) * ldH + N + i] += two_over_lam * (ci * ci);
+  g[i] += -(two_over_lam * si);
+  g[N + i] += two_over_lam * (ci * si);
+}
+
 __global__ void axpy_kernel(double* __restrict__ z, const double* __restrict__ d, double step, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) z[i] = z[i] - step * d[i];
@@ -248,6 +275,7 @@ void set_kind(GnState& g) {
   auto K = [&](int s, int p, int q) { g.coef_kind[s][p][q] = 1; };
   switch (g.pde) {
     case PDE_ELLIPTIC: K(0, 0, 0); K(0, 1, 0); break;
+    case PDE_ELLIPTIC_RELAXED: K(0, 0, 0); K(0, 1, 1); break;
     case PDE_BURGERS: K(0, 0, 0); K(0, 0, 1); K(0, 0, 2); K(0, 1, 1); K(0, 2, 2); K(0, 3, 0); break;
     case PDE_EIKONAL: K(0, 0, 1); K(0, 1, 2); K(0, 2, 1); K(0, 2, 2); K(0, 3, 0); break;
     case PDE_DARCY:
@@ -288,9 +316,14 @@ static int eval_loss_device(gpp_handle* h, const double* d_z, bool with_coef) {
     if (rc) return rc;
   }
   const bool darcy = g.pde == PDE_DARCY;
-  sumsq_kernel<<<1, 1024, 0, h->stream>>>(g.s[0], h->slot[0].M, darcy ? g.s[1] : nullptr, darcy ? h->slot[1].M : 0,
-                                          darcy ? d_z + 3 * (long)h->N : nullptr, g.data_u, darcy ? g.N_data : 0,
-                                          darcy ? 1.0 / (g.noise * g.noise) : 0.0, g.scal);
+  if (g.pde == PDE_ELLIPTIC_RELAXED) {
+    const double* ss2 = g.coef + ((long)((1 * GPP_MAX_BLOCKS + 0) * GPP_MAX_ZBLOCKS + 0)) * h->N;
+    sumsq_kernel<<<1, 1024, 0, h->stream>>>(g.s[0], h->slot[0].M, nullptr, 0, ss2, nullptr, h->N, 1.0 / g.params[3], g.scal);
+  } else {
+    sumsq_kernel<<<1, 1024, 0, h->stream>>>(g.s[0], h->slot[0].M, darcy ? g.s[1] : nullptr, darcy ? h->slot[1].M : 0,
+                                            darcy ? d_z + 3 * (long)h->N : nullptr, g.data_u, darcy ? g.N_data : 0,
+                                            darcy ? 1.0 / (g.noise * g.noise) : 0.0, g.scal);
+  }
   h->launches++;
   CUDA_TRY(h, cudaGetLastError());
   return GPP_OK;
@@ -361,6 +394,12 @@ int gn_step(gpp_handle* h, double step, double* loss_host) {
     hess_kernel<<<grid, 256, 0, h->stream>>>(a);
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
+  }
+  if (g.pde == PDE_ELLIPTIC_RELAXED) {
+    const double* ss2 = g.coef + ((long)((1 * GPP_MAX_BLOCKS + 0) * GPP_MAX_ZBLOCKS + 0)) * N;
+    const double* cc = g.coef + ((long)((1 * GPP_MAX_BLOCKS + 0) * GPP_MAX_ZBLOCKS + 1)) * N;
+    relax_penalty_kernel<<<(N + 255) / 256, 256, 0, h->stream>>>(N, 2.0 / g.params[3], ss2, cc, g.H, g.ldH, g.g);
+    h->launches++;
   }
   mark(2);
   // delta = H^{-1} g via Cholesky (H is SPD: 2 S^T S + data term)

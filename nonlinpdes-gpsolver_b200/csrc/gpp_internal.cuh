@@ -18,7 +18,7 @@ enum { OP_ID = 0, OP_D1 = 1, OP_D2 = 2, OP_D22 = 3, OP_LAP = 4 };
 // layouts
 enum { LAY_ELLIPTIC = 0, LAY_BURGERS = 1, LAY_EIKONAL = 2, LAY_DARCY_A = 3 };
 // PDE ids for the GN step
-enum { PDE_ELLIPTIC = 0, PDE_BURGERS = 1, PDE_EIKONAL = 2, PDE_DARCY = 3 };
+enum { PDE_ELLIPTIC = 0, PDE_BURGERS = 1, PDE_EIKONAL = 2, PDE_DARCY = 3, PDE_ELLIPTIC_RELAXED = 4 };
 
 struct Layout {
   int nblk;

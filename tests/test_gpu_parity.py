@@ -265,3 +265,68 @@ def test_sampling_bit_exact(pkg):
         np.random.seed(42)
         b = o.sampled_pts_rdm(100, 31, dom, time_dependent=td)
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_relaxed_gn_matches_oracle(pkg):
+    """GN_relaxed_method (src/PDEs.py:137-201): unknowns [v; w], penalised constraint."""
+    np.random.seed(2)
+    N, Nb = 300, 60
+    Xd, Xb = o.sampled_pts_rdm(N, Nb, DOM)
+    init = np.random.normal(0.0, 1.0, 2 * N)
+    lam = 1e-6
+    ref = o.Nonlinear_elliptic2d(alpha=1.0, m=3)
+    ref.set_points(Xd, Xb, o.elliptic_f(Xd[:, 0], Xd[:, 1]), o.elliptic_u(Xb[:, 0], Xb[:, 1]))
+    ref.Gram_matrix("Gaussian", 0.2, 1e-6, "adaptive")
+    ref.Gram_Cholesky("lu")
+    ref.GN_relaxed_method(4, 1, init, pen_lambda=lam)
+    p = pkg["PDEs"].Nonlinear_elliptic2d(alpha=1.0, m=3, bdy=o.elliptic_u, rhs=o.elliptic_f)
+    p.get_sampled_points(Xd, Xb)
+    p.Gram_matrix("Gaussian", 0.2, 1e-6, "adaptive")
+    p.Gram_Cholesky()
+    p.GN_relaxed_method(4, 1, init, pen_lambda=lam, print_hist=False)
+    np.testing.assert_allclose(p.loss_hist, ref.loss_hist, rtol=1e-6)
+    np.testing.assert_allclose(p.sol_sampled_pts, ref.sol_sampled_pts, atol=1e-6 * np.max(np.abs(ref.sol_sampled_pts)))
+    assert p.sol_vec.shape == (2 * N + Xb.shape[0],)
+    np.testing.assert_allclose(p.loss_relaxed(init, lam), ref.loss_hist[0], rtol=1e-9)
+
+
+def test_darcy_residual_bit_exact_with_shared_exp(pkg):
+    """Darcy's exp(-w0) uses one explicit-FMA algorithm on host (oracle/gpp_exp_ref.c) and device (gn.cu):
+    residual and linearisation coefficients are bit-exact; and that exp is within 1 ulp of numpy's."""
+    import ctypes
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = ctypes.CDLL(os.path.join(root, "oracle", "libgpp_exp_ref.so"))
+    dp = ctypes.POINTER(ctypes.c_double)
+    lib.gpp_exp_ref_array.argtypes = [dp, dp, ctypes.c_long]
+
+    def gexp(x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        out = np.empty_like(x)
+        lib.gpp_exp_ref_array(x.ctypes.data_as(dp), out.ctypes.data_as(dp), x.size)
+        return out
+
+    np.random.seed(4)
+    N, Nb, nd = 250, 40, 30
+    Xd, Xb = o.sampled_pts_rdm(N, Nb, DOM)
+    rhs_f, bdy_g = np.random.standard_normal(N), np.random.standard_normal(Xb.shape[0])
+    data_u = np.random.standard_normal(nd)
+    eng = pkg["lib"].Engine()
+    eng.set_points(Xd, Xb)
+    eng.gram_assemble(0, "Darcy_flow2d", "Gaussian", 0.2)
+    eng.gram_assemble(1, "Darcy_flow2d_a", "Gaussian", 0.2)
+    eng.gn_setup("Darcy_flow2d", [], rhs_f, bdy_g, data_u, 1e-3)
+    z = np.random.standard_normal(6 * N) * 2
+    eng.gn_set_z(z)
+    w0, w1, w2, v0, v1, v2 = [z[k * N:(k + 1) * N] for k in range(6)]
+    ew = gexp(-w0)
+    v3 = -v1 * w1 - v2 * w2 + (-rhs_f) * ew                  # src/InverseProblems.py:114 with the shared exp
+    assert np.array_equal(eng.gn_residual(0), np.concatenate([v1, v2, v3, v0, bdy_g]))
+    assert np.array_equal(eng.gn_residual(1), np.concatenate([w1, w2, w0]))
+    expect = {(0, 2, 0): (-rhs_f) * (-ew), (0, 2, 1): -v1, (0, 2, 2): -v2, (0, 2, 4): -w1, (0, 2, 5): -w2,
+              (0, 0, 4): np.ones(N), (0, 1, 5): np.ones(N), (0, 3, 3): np.ones(N), (1, 0, 1): np.ones(N), (1, 1, 2): np.ones(N),
+              (1, 2, 0): np.ones(N)}
+    for (s, p, q), c in expect.items():
+        got, present = eng.gn_coef(s, p, q)
+        assert present and np.array_equal(got, c), (s, p, q)
+    assert np.max(np.abs(ew - np.exp(-w0)) / np.spacing(np.exp(-w0))) <= 1.0
+    eng.close()
