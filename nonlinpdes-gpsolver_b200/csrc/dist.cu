@@ -14,6 +14,7 @@
 #include <nccl.h>
 
 #include <cstring>
+#include <vector>
 
 namespace {
 
@@ -25,7 +26,8 @@ struct DistState {
   long ld = 0;
   int M = 0, nloc = 0;          // global size, local row count
   CUtensorMap mapLoc;
-  double* rowbuf = nullptr;     // NB x M staging of the broadcast block row
+  double* rowbuf = nullptr;     // NB x M staging of the broadcast block row (two buffers alternate)
+  double* rowbuf2 = nullptr;
   double* dvec = nullptr;       // M doubles scratch
   bool factored = false;
 };
@@ -90,6 +92,7 @@ int gpp_dist_finalize(gpp_handle* h) {
   if (d->comm) ncclCommDestroy(d->comm);
   if (d->Tloc) cudaFree(d->Tloc);
   if (d->rowbuf) cudaFree(d->rowbuf);
+  if (d->rowbuf2) cudaFree(d->rowbuf2);
   if (d->dvec) cudaFree(d->dvec);
   delete d;
   h->dist = nullptr;
@@ -120,10 +123,12 @@ int gpp_dist_gram_assemble(gpp_handle* h, int layout, int kernel, const double* 
   if (!d->Tloc || d->M != M || d->nloc != nloc) {
     if (d->Tloc) cudaFree(d->Tloc);
     if (d->rowbuf) cudaFree(d->rowbuf);
+    if (d->rowbuf2) cudaFree(d->rowbuf2);
     if (d->dvec) cudaFree(d->dvec);
     d->M = M; d->nloc = nloc; d->ld = ld;
     CUDA_TRY(h, cudaMalloc(&d->Tloc, sizeof(double) * (size_t)(nloc > 0 ? nloc : 1) * ld));
     CUDA_TRY(h, cudaMalloc(&d->rowbuf, sizeof(double) * (size_t)NB * ld));
+    CUDA_TRY(h, cudaMalloc(&d->rowbuf2, sizeof(double) * (size_t)NB * ld));
     CUDA_TRY(h, cudaMalloc(&d->dvec, sizeof(double) * (size_t)M));
     if (nloc > 0) {
       int rc = make_tensor_map(h, &d->mapLoc, d->Tloc, nloc, M, ld);
@@ -184,7 +189,61 @@ int gpp_dist_add_diag(gpp_handle* h, const double* add) {
   return GPP_OK;
 }
 
+// Update + solve + own-diagonal update of local rows [lrow, lrow + nrows) in block column j against the received block
+// row (rowbuf holds L[j, 0:(j+1)NB] packed with leading dimension ldrow), on h->cur.
+static int dist_step_rows(gpp_handle* h, DistState* d, int j, int lrow, int nrows, double* rowbuf) {
+  if (nrows <= 0) return GPP_OK;
+  const int NB = h->NB, M = d->M;
+  const int j0 = j * NB;
+  const int nbj = (M - j0 < NB) ? (M - j0) : NB;
+  const long ldrow = j0 + NB;
+  Mat Mloc{d->Tloc, d->ld, &d->mapLoc};
+  CUtensorMap mapRow;
+  int rc = make_tensor_map(h, &mapRow, rowbuf, nbj, j0 + nbj, ldrow);
+  if (rc) return rc;
+  if (j > 0) {
+    GemmDesc g{};
+    g.mapA = &d->mapLoc; g.mapB = &mapRow;
+    g.a_row0 = lrow; g.b_row0 = 0;
+    g.C = d->Tloc + (long)lrow * d->ld + j0; g.ldc = d->ld; g.Cin = g.C; g.ldcin = d->ld;
+    g.m = nrows; g.n = nbj; g.k0 = 0; g.k1 = j0; g.kb_off = 0; g.alpha = -1.0; g.lower_only = 0;
+    rc = gemm_nt_launch(h, g);
+    if (rc) return rc;
+  }
+  Mat Row{rowbuf, ldrow, &mapRow};
+  rc = trsm_right_lt(h, Mloc, lrow, j0, nrows, Row, 0, j0, nbj);
+  if (rc) return rc;
+  // right-looking update of this rank's own diagonal blocks with the freshly solved column j: keeps every diagonal
+  // block up to date (in column order), so its owner can factorise it the moment its turn comes
+  GemmDesc g{};
+  g.mapA = &d->mapLoc; g.mapB = &d->mapLoc;
+  g.C = d->Tloc; g.ldc = d->ld; g.Cin = d->Tloc; g.ldcin = d->ld;
+  g.k0 = j0; g.k1 = j0 + nbj; g.kb_off = 0; g.alpha = -1.0;
+  g.bd_count = (nrows + NB - 1) / NB; g.bd_world = d->world; g.bd_rank = d->rank; g.bd_lblk0 = lrow / NB; g.bd_nb = NB; g.bd_M = M;
+  return gemm_nt_launch(h, g);
+}
+
+// factorise the (up-to-date) diagonal block of block row j and pack L[j, 0:(j+1)NB] into rowbuf, on h->cur
+static int dist_factor_and_pack(gpp_handle* h, DistState* d, int j, double* rowbuf) {
+  const int NB = h->NB, M = d->M, P = d->world;
+  const int j0 = j * NB;
+  const int nbj = (M - j0 < NB) ? (M - j0) : NB;
+  const long ldrow = j0 + NB;
+  const int lr = local_blk(j, P) * NB;
+  Mat Mloc{d->Tloc, d->ld, &d->mapLoc};
+  int rc = potrf_diag(h, Mloc, lr, j0, nbj, j0);
+  if (rc) return rc;
+  CUDA_TRY(h, cudaMemcpy2DAsync(rowbuf, ldrow * 8, d->Tloc + (long)lr * d->ld, d->ld * 8, (size_t)(j0 + nbj) * 8, nbj,
+                                cudaMemcpyDeviceToDevice, h->cur));
+  return GPP_OK;
+}
+
 // Distributed X.Gram_Cholesky (src/PDEs.py:75-80).  *info as in gpp_potrf, identical on every rank.
+//
+// Look-ahead: the owner of block row j+1 treats that block row first (high-priority stream sP): update + solve in
+// column j, factorise its diagonal block, pack, broadcast -- while every rank is still busy with the bulk of
+// column j on the main stream.  Two row buffers alternate; events order bulk(j) after bcast(j) and bcast(j+2) after
+// bulk(j).  NCCL calls are issued in the same order (j = 0, 1, ...) on the side stream of every rank.
 int gpp_dist_potrf(gpp_handle* h, int* info) {
   if (!h || !h->dist) return -1;
   DistState* d = ds(h);
@@ -193,56 +252,89 @@ int gpp_dist_potrf(gpp_handle* h, int* info) {
   CUDA_TRY(h, cudaSetDevice(h->device));
   const int NB = h->NB, P = d->world, M = d->M, rank = d->rank;
   const int nblk = (M + NB - 1) / NB;
-  Mat Mloc{d->Tloc, d->ld, &d->mapLoc};
-  CUDA_TRY(h, cudaMemsetAsync(h->d_info, 0, sizeof(int), h->stream));
-  h->cur = h->stream;
-  for (int j = 0; j < nblk; ++j) {
+  cudaStream_t S = h->stream, Sp = h->sP;
+  double* rb[2] = {d->rowbuf, d->rowbuf2};
+  CUDA_TRY(h, cudaMemsetAsync(h->d_info, 0, sizeof(int), S));
+  size_t used = 0;
+  auto new_event = [&]() {
+    if (used == h->evpool.size()) {
+      cudaEvent_t e;
+      cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+      h->evpool.push_back(e);
+    }
+    return h->evpool[used++];
+  };
+  constexpr int NREG = 3;
+  auto clampi = [&](long v) { return (int)(v > d->nloc ? d->nloc : v); };
+  const int bound[NREG + 1] = {0, clampi(round_up(d->nloc / 2, NB)), clampi(round_up((3L * d->nloc) / 4, NB)), d->nloc};
+  std::vector<cudaEvent_t> ev_bc(nblk), ev_bulk(NREG * nblk);
+  cudaEvent_t ev0 = new_event();
+  CUDA_TRY(h, cudaEventRecord(ev0, S));
+  CUDA_TRY(h, cudaStreamWaitEvent(Sp, ev0, 0));
+  for (int k = 0; k < 2; ++k) CUDA_TRY(h, cudaStreamWaitEvent(h->sG[k], ev0, 0));
+  auto bcast = [&](int j) -> int {     // on Sp
     const int j0 = j * NB;
     const int nbj = (M - j0 < NB) ? (M - j0) : NB;
-    const int own = owner_of(j, P);
-    const long ldrow = j0 + NB;                // packed row length (multiple of 16)
-    if (rank == own) {
-      const int lr = local_blk(j, P) * NB;
-      if (j > 0) {                             // diagonal block: C[j,j] -= L[j,0:j] L[j,0:j]^T
-        GemmDesc g{};
-        g.mapA = &d->mapLoc; g.mapB = &d->mapLoc;
-        g.a_row0 = lr; g.b_row0 = lr;
-        g.C = d->Tloc + (long)lr * d->ld + j0; g.ldc = d->ld; g.Cin = g.C; g.ldcin = d->ld;
-        g.m = nbj; g.n = nbj; g.k0 = 0; g.k1 = j0; g.kb_off = 0; g.alpha = -1.0; g.lower_only = 1;
-        int rc = gemm_nt_launch(h, g);
-        if (rc) return rc;
+    if (P > 1) NCCL_TRY(h, ncclBroadcast(rb[j & 1], rb[j & 1], (size_t)nbj * (j0 + NB), ncclDouble, owner_of(j, P), d->comm, Sp));
+    ev_bc[j] = new_event();
+    CUDA_TRY(h, cudaEventRecord(ev_bc[j], Sp));
+    return GPP_OK;
+  };
+  int rc = GPP_OK;
+  // prologue: block row 0
+  h->cur = Sp;
+  if (rank == owner_of(0, P)) rc = dist_factor_and_pack(h, d, 0, rb[0]);
+  if (!rc) rc = bcast(0);
+  for (int j = 0; j < nblk && !rc; ++j) {
+    const int lstart = owned_upto(j, rank, P) * NB;        // first local row below block row j
+    int bulk_start = lstart;
+    if (j + 1 < nblk) {
+      // rb[(j+1)&1] was last read by bulk(j-1); block row j+1's earlier columns were written by bulk(<= j-1)
+      if (j >= 1) {
+        for (int k = 0; k < NREG; ++k) CUDA_TRY(h, cudaStreamWaitEvent(Sp, ev_bulk[NREG * (j - 1) + k], 0));
       }
-      int rc = potrf_diag(h, Mloc, lr, j0, nbj, j0);
-      if (rc) return rc;
-      CUDA_TRY(h, cudaMemcpy2DAsync(d->rowbuf, ldrow * 8, d->Tloc + (long)lr * d->ld, d->ld * 8, (size_t)(j0 + nbj) * 8, nbj,
-                                    cudaMemcpyDeviceToDevice, h->stream));
+      if (rank == owner_of(j + 1, P)) {
+        h->cur = Sp;
+        const int nb1 = (M - (j + 1) * NB < NB) ? (M - (j + 1) * NB) : NB;
+        rc = dist_step_rows(h, d, j, lstart, nb1, rb[j & 1]);   // block row j+1 is this rank's first row block below j
+        if (!rc) rc = dist_factor_and_pack(h, d, j + 1, rb[(j + 1) & 1]);
+        if (rc) break;
+        bulk_start = lstart + NB;
+      }
+      rc = bcast(j + 1);
+      if (rc) break;
     }
-    if (P > 1) NCCL_TRY(h, ncclBroadcast(d->rowbuf, d->rowbuf, (size_t)nbj * ldrow, ncclDouble, own, d->comm, h->stream));
-    // rows below j owned by this rank are contiguous in local storage
-    const int lstart = owned_upto(j, rank, P) * NB;
-    const int mrows = d->nloc - lstart;
-    if (mrows > 0) {
-      CUtensorMap mapRow;
-      int rc = make_tensor_map(h, &mapRow, d->rowbuf, nbj, j0 + nbj, ldrow);
-      if (rc) return rc;
-      if (j > 0) {
-        GemmDesc g{};
-        g.mapA = &d->mapLoc; g.mapB = &mapRow;
-        g.a_row0 = lstart; g.b_row0 = 0;
-        g.C = d->Tloc + (long)lstart * d->ld + j0; g.ldc = d->ld; g.Cin = g.C; g.ldcin = d->ld;
-        g.m = mrows; g.n = nbj; g.k0 = 0; g.k1 = j0; g.kb_off = 0; g.alpha = -1.0; g.lower_only = 0;
-        rc = gemm_nt_launch(h, g);
-        if (rc) return rc;
-      }
-      Mat Row{d->rowbuf, ldrow, &mapRow};
-      rc = trsm_right_lt(h, Mloc, lstart, j0, mrows, Row, 0, j0, nbj);
-      if (rc) return rc;
+    // bulk of column j: the remaining rows, cut at fixed local-row boundaries into regions that stay on the same
+    // stream for the whole factorisation.  A row only depends on its own history and on the received block row, so
+    // region A may start column j+1 while region B still finishes column j: the second stream fills the SMs the last
+    // wave of the other one leaves idle.
+    for (int k = 0; k < NREG && !rc; ++k) {
+      const int lo = bulk_start > bound[k] ? bulk_start : bound[k];
+      const int hi = bound[k + 1];
+      cudaStream_t sg = h->sG[k & 1];
+      CUDA_TRY(h, cudaStreamWaitEvent(sg, ev_bc[j], 0));
+      h->cur = sg;
+      if (hi > lo) rc = dist_step_rows(h, d, j, lo, hi - lo, rb[j & 1]);
+      ev_bulk[NREG * j + k] = new_event();
+      CUDA_TRY(h, cudaEventRecord(ev_bulk[NREG * j + k], sg));
     }
   }
-  if (P > 1) NCCL_TRY(h, ncclAllReduce(h->d_info, h->d_info, 1, ncclInt, ncclMax, d->comm, h->stream));
+  h->cur = S;
+  if (rc) return rc;
+  {
+    cudaEvent_t e = new_event();
+    CUDA_TRY(h, cudaEventRecord(e, Sp));
+    CUDA_TRY(h, cudaStreamWaitEvent(S, e, 0));
+    for (int k = 0; k < 2; ++k) {
+      cudaEvent_t eg = new_event();
+      CUDA_TRY(h, cudaEventRecord(eg, h->sG[k]));
+      CUDA_TRY(h, cudaStreamWaitEvent(S, eg, 0));
+    }
+  }
+  if (P > 1) NCCL_TRY(h, ncclAllReduce(h->d_info, h->d_info, 1, ncclInt, ncclMax, d->comm, S));
   int hinfo = 0;
-  CUDA_TRY(h, cudaMemcpyAsync(&hinfo, h->d_info, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(&hinfo, h->d_info, sizeof(int), cudaMemcpyDeviceToHost, S));
+  CUDA_TRY(h, cudaStreamSynchronize(S));
   if (info) *info = hinfo;
   d->factored = true;
   return GPP_OK;

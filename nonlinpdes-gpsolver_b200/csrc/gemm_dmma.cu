@@ -32,6 +32,9 @@ struct GemmParams {
   double alpha;
   int lower_only;
   int tiles_m, tiles_n;
+  // block-diagonal batch mode (multi-GPU Cholesky): tile t -> local block row bd_lblk0 + t / ntri, lower tile t % ntri of
+  // the NB x NB diagonal block of that block row; global column of the block = ((lblk * bd_world) + bd_rank) * bd_nb
+  int bd_mode, bd_world, bd_rank, bd_lblk0, bd_nb, bd_M;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -95,10 +98,28 @@ gemm_nt_dmma_kernel(const __grid_constant__ GemmParams p) {
     tm = blockIdx.x / p.tiles_n;
     tn = blockIdx.x % p.tiles_n;
   }
-  const int row_base = tm * BM;    // within the output block
-  const int col_base = tn * BN;
-  const int a_row = p.a_row0 + row_base;
-  const int b_row = p.b_row0 + col_base;
+  int row_base = tm * BM;    // within the output block
+  int col_base = tn * BN;
+  int a_row = p.a_row0 + row_base;
+  int b_row = p.b_row0 + col_base;
+  double* Cp = p.C;
+  const double* Cinp = p.Cin;
+  int m_lim = p.m, n_lim = p.n;
+  if (p.bd_mode) {
+    const int nt = p.bd_nb / BM, ntri = nt * (nt + 1) / 2;
+    const int lblk = p.bd_lblk0 + blockIdx.x / ntri;
+    int tri = blockIdx.x % ntri, ti = 0;
+    while ((ti + 1) * (ti + 2) / 2 <= tri) ++ti;
+    const int tj = tri - ti * (ti + 1) / 2;
+    const int gcol0 = (lblk * p.bd_world + p.bd_rank) * p.bd_nb;      // global index of the block's first row / column
+    row_base = ti * BM; col_base = tj * BN;
+    a_row = lblk * p.bd_nb + row_base;                                // local rows of both operands
+    b_row = lblk * p.bd_nb + col_base;
+    Cp = p.C + (long)(lblk * p.bd_nb) * p.ldc + gcol0;
+    Cinp = Cp;
+    m_lim = n_lim = (p.bd_M - gcol0 < p.bd_nb) ? (p.bd_M - gcol0) : p.bd_nb;
+    if (row_base >= m_lim || col_base >= n_lim) return;
+  }
 
   int k_lo = p.k0;
   if (p.ktri) {
@@ -150,7 +171,7 @@ gemm_nt_dmma_kernel(const __grid_constant__ GemmParams p) {
   // value is the remainder Cin - sum_k a b (same order as a right-looking update).  For the nearly singular
   // Gram matrices of this solver the remainder shrinks quickly with k, and rounding each partial result
   // relative to the remainder -- not to the partial sum -- is what keeps pivots of size ~nugget positive.
-  const bool progressive = (p.Cin != nullptr) && (p.alpha == 1.0 || p.alpha == -1.0);
+  const bool progressive = (Cinp != nullptr) && (p.alpha == 1.0 || p.alpha == -1.0);
   if (progressive) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -158,10 +179,10 @@ gemm_nt_dmma_kernel(const __grid_constant__ GemmParams p) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int cc = col_base + wn * 32 + j * 8 + 2 * t;
-        if (r < p.m && cc < p.n) {
-          const double* src = p.Cin + (long)r * p.ldcin + cc;
+        if (r < m_lim && cc < n_lim) {
+          const double* src = Cinp + (long)r * p.ldcin + cc;
           acc[i][j][0] = p.alpha * src[0];
-          if (cc + 1 < p.n) acc[i][j][1] = p.alpha * src[1];
+          if (cc + 1 < n_lim) acc[i][j][1] = p.alpha * src[1];
         }
       }
     }
@@ -201,16 +222,16 @@ gemm_nt_dmma_kernel(const __grid_constant__ GemmParams p) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int r = row_base + wm * 32 + i * 8 + g;
-    if (r >= p.m) continue;
+    if (r >= m_lim) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int cc = col_base + wn * 32 + j * 8 + 2 * t;
-      if (cc >= p.n) continue;
+      if (cc >= n_lim) continue;
       double v0 = p.alpha * acc[i][j][0], v1 = p.alpha * acc[i][j][1];
-      double* dst = p.C + (long)r * p.ldc + cc;
-      const bool two = (cc + 1 < p.n);
-      if (p.Cin && !progressive) {
-        const double* src = p.Cin + (long)r * p.ldcin + cc;
+      double* dst = Cp + (long)r * p.ldc + cc;
+      const bool two = (cc + 1 < n_lim);
+      if (Cinp && !progressive) {
+        const double* src = Cinp + (long)r * p.ldcin + cc;
         v0 += src[0];
         if (two) v1 += src[1];
       }
@@ -252,7 +273,7 @@ int make_tensor_map(gpp_handle* h, CUtensorMap* map, const double* base, long ro
 }
 
 int gemm_nt_launch(gpp_handle* h, const GemmDesc& d) {
-  if (d.m <= 0 || d.n <= 0) return GPP_OK;
+  if (d.bd_count <= 0 && (d.m <= 0 || d.n <= 0)) return GPP_OK;
   static bool attr_set = false;
   if (!attr_set) {
     CUDA_TRY(h, cudaFuncSetAttribute(gemm_nt_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -272,8 +293,12 @@ int gemm_nt_launch(gpp_handle* h, const GemmDesc& d) {
   p.alpha = d.alpha; p.lower_only = d.lower_only;
   p.tiles_m = (d.m + BM - 1) / BM;
   p.tiles_n = (d.n + BN - 1) / BN;
+  p.bd_mode = d.bd_count > 0; p.bd_world = d.bd_world; p.bd_rank = d.bd_rank; p.bd_lblk0 = d.bd_lblk0; p.bd_nb = d.bd_nb; p.bd_M = d.bd_M;
   long ntiles;
-  if (d.lower_only) {
+  if (p.bd_mode) {
+    const int nt = d.bd_nb / BM;
+    ntiles = (long)d.bd_count * (nt * (nt + 1) / 2);
+  } else if (d.lower_only) {
     // square lower-triangular tile set (requires a_row0 == b_row0 and m == n)
     ntiles = (long)p.tiles_m * (p.tiles_m + 1) / 2;
   } else {

@@ -140,6 +140,9 @@ struct GemmDesc {
   int diag_nb;                  // block size of the clean diagonal blocks (NB)
   double alpha;
   int lower_only;               // skip tiles strictly above the diagonal (uses global row/col = a_row0+i, b_row0+j)
+  // block-diagonal batch (multi-GPU Cholesky): bd_count diagonal blocks of the row-sharded matrix, one per owned block
+  // row starting at local block bd_lblk0: C_blk -= A_blk[:, k0:k1] A_blk[:, k0:k1]^T (lower tiles).  0 = off.
+  int bd_count, bd_world, bd_rank, bd_lblk0, bd_nb, bd_M;
 };
 int gemm_nt_launch(gpp_handle* h, const GemmDesc& d);
 int make_tensor_map(gpp_handle* h, CUtensorMap* map, const double* base, long rows, long cols, long ld);
