@@ -30,6 +30,10 @@ sys.path.insert(0, ROOT)
 
 FP64_PEAK_FALLBACK_TFLOPS = 36.19   # cuBLAS DGEMM 8192^3 on this pool's B200 (profiles/r01_cublas_dgemm_cusolver_potrf.txt)
 HBM_PEAK_FALLBACK_GBS = 6650.0      # B200_PROFILING.md fallback
+# dram__bytes_read.sum + dram__bytes_write.sum of one large left-looking update launch (628 tiles, K=20480;
+# algorithmic operand bytes 3.70e9), from the ncu --set full capture profiles/r01_gemm_big_N20k.ncu-rep
+NCU_GEMM_TRAFFIC = {"bytes_per_launch": 3.715e9 + 0.098e9, "algorithmic_bytes_per_launch": 3.70e9,
+                    "launch": "gemm_nt_dmma_kernel 628 tiles K=20480 (N_domain=20000, block column 40)", "source": "profiles/r01_ncu_summary.md"}
 
 
 def u_true(x1, x2):
@@ -126,6 +130,11 @@ def cpu_port_sample(N_sample, gn_steps, nugget, workload_M, workload_n):
     bounded sample and extrapolates to the workload with the reference's dense flop model."""
     from oracle import gp_oracle as o
     cores = os.cpu_count() or 1
+    try:  # torchrun exports OMP_NUM_THREADS=1: give the CPU arm every host thread it can use
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=cores)
+    except Exception:
+        pass
     np.random.seed(0)
     Nb = n_boundary_for(N_sample)
     Xd, Xb = o.sampled_pts_rdm(N_sample, Nb, np.array([[0.0, 1.0], [0.0, 1.0]]))
@@ -263,9 +272,10 @@ def main():
     s = solver_GP(cfg, PDE_type="Nonlinear_elliptic")
     s.eqn = prob
     Xd_host, Xb_host = prob.X_domain.copy(), prob.X_boundary.copy()
+    e2e_steps = min(a.steps, 2)                   # bounded: the e2e loop repeats whole solves
     barrier()
     t0 = time.perf_counter()
-    for _ in range(a.steps):
+    for _ in range(e2e_steps):
         s.get_sample(Xd_host, Xb_host, print_option=False)          # H2D: points; evaluates rhs_f, bdy_g on host
         s.solve(print_option=False)                                  # H2D: data vectors, z0, nugget; D2H: diag, loss, z, sol_vec
         s.collocation_pts_err(u_true(Xd_host[:, 0], Xd_host[:, 1]), print_option=False)
@@ -275,7 +285,7 @@ def main():
         tt = torch.tensor([e2e_elapsed], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_elapsed = float(tt.item())
-    e2e_value = world * a.gn_steps * a.steps / e2e_elapsed
+    e2e_value = world * a.gn_steps * e2e_steps / e2e_elapsed
     h2d = 8 * (2 * (N + Nb) + N + Nb + n + M)                        # points, rhs_f, bdy_g, z0, nugget diag
     d2h = 8 * (M + (a.gn_steps + 1) + n + M)                         # diag, losses, z, sol_vec
 
@@ -298,13 +308,14 @@ def main():
                        "algorithm": "potrf + interior inverse once, then O(n^2) Hessian assembly + n x n potrf per GN step"},
             "phases_ms": {"assembly": T_asm, "potrf": T_potrf, "inverse": T_inv, "gn_total": T_gn, "gn_per_step": T_gn / a.gn_steps},
             "roofline": {"kernel": "gemm_nt_dmma_kernel (potrf + inverse phases, M^3 algorithmic flops)", "bound": "tensor",
-                         "achieved": gemm_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": gemm_tf / fp64_peak, "traffic": None,
+                         "achieved": gemm_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": gemm_tf / fp64_peak,
+                         "traffic": NCU_GEMM_TRAFFIC,
                          "peak_source": fp64_how, "potrf_tflops": potrf_tf, "potrf_frac": potrf_tf / fp64_peak,
                          "inverse_tflops": 2 * M ** 3 / 3.0 / T_inv / 1e9},
             "assembly_roofline": {"kernel": "gram_assemble_kernel", "bound": "hbm", "achieved": asm_bytes / T_asm / 1e6, "peak": hbm,
                                   "unit": "GB/s", "frac": asm_bytes / T_asm / 1e6 / hbm, "peak_source": hbm_how},
             "e2e": {"value": e2e_value, "unit": "GN steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": 1e3 * e2e_elapsed / a.steps},
+                    "ms_per_step": 1e3 * e2e_elapsed / e2e_steps, "steps": e2e_steps},
             "gpu_launches": int(launches), "clocks": clocks,
             "result": {"final_loss": final_loss, "pts_L2_err": float(np.sqrt(np.mean(err ** 2))), "pts_max_err": float(err.max()),
                        "chol_info": prob.chol_info},

@@ -83,6 +83,9 @@ int gpp_gn_get_z(gpp_handle* h, double* z);
 int gpp_gn_loss(gpp_handle* h, double* loss);
 /* one iteration of X.GN_method's loop body  src/PDEs.py:117-120: z <- z - step * H^{-1} g, returns loss(z) */
 int gpp_gn_step(gpp_handle* h, double step_size, double* loss);
+/* X.grad_loss(z) and X.Hessian_GN(z, z)  src/PDEs.py:90-91,101-102 at the current z (either pointer may be NULL);
+ * grad_out[n], hess_out[n x n] row-major with n = (#unknown blocks) * N.  Needs gpp_inverse. */
+int gpp_gn_grad_hess(gpp_handle* h, double* grad_out, double* hess_out);
 /* F(z) of slot (the reference's sol_vec, src/PDEs.py:132-133) at the current z */
 int gpp_gn_residual(gpp_handle* h, int slot, double* F_out);
 /* Jacobian coefficient vector c_pq (length N) of slot at the current z; returns 1 in *present if nonzero */

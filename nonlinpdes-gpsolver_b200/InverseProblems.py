@@ -76,10 +76,17 @@ class Darcy_flow2d(_GPProblem):
         eng.timer_start()
         self.chol_info = (eng.potrf(0), eng.potrf(1))
         self.timings['potrf_ms'] = eng.timer_stop()
+        self._inverted = False
         self._state = 'chol'
 
     def _setup_gn(self):
         self._engine().gn_setup('Darcy_flow2d', [], self.rhs_f, self.bdy_g, self.data_u, self.noise_level)
+
+    def _ensure_inverse(self):
+        if not getattr(self, '_inverted', False):
+            self._engine().inverse(0)
+            self._engine().inverse(1)
+            self._inverted = True
 
     def GN_method(self, max_iter=3, step_size=1, initial_sol='rdm', print_hist=True):
         """src/InverseProblems.py:153-186."""
@@ -92,6 +99,7 @@ class Darcy_flow2d(_GPProblem):
         eng.inverse(0)
         eng.inverse(1)
         self.timings['inverse_ms'] = eng.timer_stop()
+        self._inverted = True
         eng.gn_set_z(sol)
         eng.timer_start()
         loss_now = eng.gn_loss()

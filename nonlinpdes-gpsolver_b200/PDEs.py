@@ -125,6 +125,7 @@ class _GPProblem(object):
         eng.timer_start()
         self.chol_info = eng.potrf(0)
         self.timings['potrf_ms'] = eng.timer_stop()
+        self._inverted = False
         self._state = 'chol'
 
     # ---- loss / GN ----
@@ -140,6 +141,26 @@ class _GPProblem(object):
         self._setup_gn()
         eng.gn_set_z(z)
         return eng.gn_loss()
+
+    def _at(self, z):
+        eng = self._engine()
+        self._setup_gn()
+        self._ensure_inverse()
+        eng.gn_set_z(z)
+        return eng
+
+    def _ensure_inverse(self):
+        if not getattr(self, '_inverted', False):
+            self._engine().inverse(0)
+            self._inverted = True
+
+    def grad_loss(self, z):
+        """grad(self.loss)(z)  (src/PDEs.py:90-91)."""
+        return self._at(z).gn_grad_hess(True, False)[0]
+
+    def Hessian_GN(self, z, z_old=None):
+        """hessian(GN_loss)(z, z_old) (src/PDEs.py:101-102); it depends on z_old only (Burgers takes one argument)."""
+        return self._at(z if z_old is None else z_old).gn_grad_hess(False, True)[1]
 
     def _initial_guess(self, initial_sol):
         n = self._nz * self.N_domain
@@ -162,6 +183,7 @@ class _GPProblem(object):
         eng.timer_start()
         eng.inverse(0)
         self.timings['inverse_ms'] = eng.timer_stop()
+        self._inverted = True
         eng.gn_set_z(sol)
         loss_hist = []
         eng.timer_start()

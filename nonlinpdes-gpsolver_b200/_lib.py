@@ -49,6 +49,7 @@ def _sig(lib):
         "gpp_gn_loss": [H, _dp],
         "gpp_gn_step": [H, C.c_double, _dp],
         "gpp_gn_residual": [H, C.c_int, _dp],
+        "gpp_gn_grad_hess": [H, _dp, _dp],
         "gpp_gn_coef": [H, C.c_int, C.c_int, C.c_int, _dp, _ip],
         "gpp_predict": [H, C.c_int, _dp, C.c_int, _dp, _dp],
         "gpp_theta_test": [H, C.c_int, _dp, C.c_int, _dp],
@@ -251,6 +252,13 @@ class Engine:
         v = C.c_double()
         self._ck(self._lib.gpp_gn_step(self._h, float(step), C.byref(v)), "gpp_gn_step")
         return float(v.value)
+
+    def gn_grad_hess(self, want_grad=True, want_hess=True):
+        n = self.nz * self.N
+        g = np.empty(n) if want_grad else None
+        H = np.empty((n, n)) if want_hess else None
+        self._ck(self._lib.gpp_gn_grad_hess(self._h, _ptr(g), _ptr(H)), "gpp_gn_grad_hess")
+        return g, H
 
     def gn_residual(self, slot):
         M, _ = self.gram_size(slot)

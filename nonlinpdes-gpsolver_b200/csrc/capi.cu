@@ -428,6 +428,23 @@ int gpp_gn_step(gpp_handle* h, double step, double* loss) {
   return gn_step(h, step, loss);
 }
 
+int gpp_gn_grad_hess(gpp_handle* h, double* grad_out, double* hess_out) {
+  int rc = gn_check(h, true);
+  if (rc) return rc;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  double dummy;
+  rc = gn_loss(h, h->gn.z, &dummy);            // F, s = L^{-1} F and the coefficients at the current z
+  if (rc) return rc;
+  rc = gn_grad_hess(h);
+  if (rc) return rc;
+  GnState& g = h->gn;
+  if (grad_out) CUDA_TRY(h, cudaMemcpyAsync(grad_out, g.g, sizeof(double) * g.n, cudaMemcpyDeviceToHost, h->stream));
+  if (hess_out)
+    CUDA_TRY(h, cudaMemcpy2DAsync(hess_out, (size_t)g.n * 8, g.H, g.ldH * 8, (size_t)g.n * 8, g.n, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return GPP_OK;
+}
+
 int gpp_gn_residual(gpp_handle* h, int slot, double* F_out) {
   if (!h || !h->gn.ready) return -1;
   if (bad_slot(h, slot)) return -2;

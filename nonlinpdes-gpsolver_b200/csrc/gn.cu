@@ -337,16 +337,13 @@ int gn_loss(gpp_handle* h, const double* d_z, double* loss_host) {
   return GPP_OK;
 }
 
-// One GN step at g.z; requires F, s and coef of g.z to be current (gn_loss leaves them so).
-int gn_step(gpp_handle* h, double step, double* loss_host) {
+// g = grad loss(z) and H = Hessian_GN(z, z) at g.z; requires F, s and coef of g.z to be current.
+int gn_grad_hess(gpp_handle* h) {
   GnState& g = h->gn;
   const int ns = nslots_of(g);
   const int N = h->N;
   set_kind(g);
   int rc;
-  static const bool trace = getenv("GPP_TRACE") != nullptr;
-  auto mark = [&](int k) { if (trace) cudaEventRecord(h->ev[2 + k], h->stream); };
-  mark(0);
   // t = L^{-T} s
   for (int s = 0; s < ns; ++s) {
     GramSlot& sl = h->slot[s];
@@ -354,7 +351,6 @@ int gn_step(gpp_handle* h, double step, double* loss_host) {
     rc = trsv_lower(h, sl.T, sl.ld, sl.M, g.t[s], true);
     if (rc) return rc;
   }
-  mark(1);
   // gradient
   {
     GParams a{};
@@ -401,6 +397,22 @@ int gn_step(gpp_handle* h, double step, double* loss_host) {
     relax_penalty_kernel<<<(N + 255) / 256, 256, 0, h->stream>>>(N, 2.0 / g.params[3], ss2, cc, g.H, g.ldH, g.g);
     h->launches++;
   }
+  return GPP_OK;
+}
+
+// One GN step at g.z; requires F, s and coef of g.z to be current (gn_loss leaves them so).
+int gn_step(gpp_handle* h, double step, double* loss_host) {
+  GnState& g = h->gn;
+  const int ns = nslots_of(g);
+  const int N = h->N;
+  set_kind(g);
+  int rc;
+  static const bool trace = getenv("GPP_TRACE") != nullptr;
+  auto mark = [&](int k) { if (trace) cudaEventRecord(h->ev[2 + k], h->stream); };
+  mark(0);
+  mark(1);
+  rc = gn_grad_hess(h);
+  if (rc) return rc;
   mark(2);
   // delta = H^{-1} g via Cholesky (H is SPD: 2 S^T S + data term)
   rc = potrf_lower(h, g.H, g.ldH, g.n, &g.mapH);
@@ -420,7 +432,7 @@ int gn_step(gpp_handle* h, double step, double* loss_host) {
     cudaEventSynchronize(h->ev[7]);
     float t[5];
     for (int k = 0; k < 5; ++k) cudaEventElapsedTime(&t[k], h->ev[2 + k], h->ev[3 + k]);
-    fprintf(stderr, "[gpp trace] gn_step: trsv L^T %.2f ms | grad+hess %.2f | potrf(H) %.2f | trsv H x2 + axpy %.2f | F, trsv L, loss %.2f\n",
+    fprintf(stderr, "[gpp trace] gn_step: setup %.2f ms | trsv L^T + grad + hess %.2f | potrf(H) %.2f | trsv H x2 + axpy %.2f | F, trsv L, loss %.2f\n",
             t[0], t[1], t[2], t[3], t[4]);
   }
   return rc;

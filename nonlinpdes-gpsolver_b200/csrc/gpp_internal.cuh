@@ -175,5 +175,6 @@ int gram_theta_test(gpp_handle* h, GramSlot& s, const double* d_xtest, int ntest
 int gn_eval_F(gpp_handle* h, const double* d_z, bool with_coef);
 int gn_loss(gpp_handle* h, const double* d_z, double* loss_host);
 int gn_step(gpp_handle* h, double step, double* loss_host);
+int gn_grad_hess(gpp_handle* h);
 int gram_kernel_eval(gpp_handle* h, int kernel, const double* kparams, int opx, int opy, const double* d_in, long n,
                      double* d_out);

@@ -330,3 +330,25 @@ def test_darcy_residual_bit_exact_with_shared_exp(pkg):
         assert present and np.array_equal(got, c), (s, p, q)
     assert np.max(np.abs(ew - np.exp(-w0)) / np.spacing(np.exp(-w0))) <= 1.0
     eng.close()
+
+
+def test_grad_and_hessian_match_oracle(pkg):
+    """grad_loss / Hessian_GN (src/PDEs.py:90-102) as dense arrays, elliptic and Eikonal."""
+    np.random.seed(6)
+    N, Nb = 150, 40
+    Xd, Xb = o.sampled_pts_rdm(N, Nb, DOM)
+    for ref, mk, nz in ((o.Nonlinear_elliptic2d(alpha=1.0, m=3), lambda: pkg["PDEs"].Nonlinear_elliptic2d(alpha=1.0, m=3, bdy=o.elliptic_u, rhs=o.elliptic_f), 1),
+                        (o.Eikonal(eps=0.1), lambda: pkg["PDEs"].Eikonal(eps=0.1, bdy=lambda a, b: 0, rhs=lambda a, b: 1), 3)):
+        p = mk()
+        p.get_sampled_points(Xd, Xb)
+        ref.set_points(Xd, Xb, p.rhs_f, p.bdy_g)
+        ref.Gram_matrix("Gaussian", 0.2, 1e-5, "adaptive")
+        ref.Gram_Cholesky("tri")
+        p.Gram_matrix("Gaussian", 0.2, 1e-5, "adaptive")
+        p.Gram_Cholesky()
+        z = np.random.standard_normal(nz * N)
+        g, H = p.grad_loss(z), p.Hessian_GN(z, z)
+        gr, Hr = ref.grad_loss(z), ref.Hessian_GN(z)
+        assert np.max(np.abs(g - gr)) <= 1e-6 * np.max(np.abs(gr))
+        assert np.max(np.abs(H - Hr)) <= 1e-6 * np.max(np.abs(Hr))
+        np.testing.assert_allclose(p.loss(z), ref.loss(z), rtol=1e-8)
