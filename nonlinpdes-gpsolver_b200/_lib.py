@@ -126,6 +126,9 @@ class Engine:
         nb = os.environ.get("GPP_NB")
         if nb:
             self.set_option("NB", float(nb))
+        gt = os.environ.get("GPP_GEMM_TILE")
+        if gt:
+            self.set_option("gemm_tile", float(gt))
         la = os.environ.get("GPP_LOOKAHEAD")
         if la is not None:
             self.set_option("lookahead", float(la))

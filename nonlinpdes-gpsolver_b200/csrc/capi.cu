@@ -121,6 +121,12 @@ int gpp_set_option(gpp_handle* h, const char* name, double value) {
     return GPP_OK;
   }
   if (!strcmp(name, "lookahead")) { h->lookahead = value != 0.0; return GPP_OK; }
+  if (!strcmp(name, "gemm_tile")) {
+    const int t = (int)value;
+    if (t != 0 && t != 64 && t != 128) { h->err = "gemm_tile must be 0, 64 or 128"; return -3; }
+    h->force_tile = t;
+    return GPP_OK;
+  }
   h->err = std::string("unknown option ") + name;
   return -2;
 }

@@ -253,7 +253,7 @@ static cudaEvent_t next_event(gpp_handle* h, size_t& used) {
   return h->evpool[used++];
 }
 
-int potrf_lower(gpp_handle* h, double* A, long ld, int n, const CUtensorMap* map) {
+int potrf_lower(gpp_handle* h, double* A, long ld, int n, const TMap2* map) {
   Mat M{A, ld, map};
   const int NB = h->NB;
   const int nblk = (n + NB - 1) / NB;

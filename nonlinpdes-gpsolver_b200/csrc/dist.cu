@@ -25,7 +25,7 @@ struct DistState {
   double* Tloc = nullptr;
   long ld = 0;
   int M = 0, nloc = 0;          // global size, local row count
-  CUtensorMap mapLoc;
+  TMap2 mapLoc;
   double* rowbuf = nullptr;     // NB x M staging of the broadcast block row (two buffers alternate)
   double* rowbuf2 = nullptr;
   double* dvec = nullptr;       // M doubles scratch
@@ -198,7 +198,7 @@ static int dist_step_rows(gpp_handle* h, DistState* d, int j, int lrow, int nrow
   const int nbj = (M - j0 < NB) ? (M - j0) : NB;
   const long ldrow = j0 + NB;
   Mat Mloc{d->Tloc, d->ld, &d->mapLoc};
-  CUtensorMap mapRow;
+  TMap2 mapRow;
   int rc = make_tensor_map(h, &mapRow, rowbuf, nbj, j0 + nbj, ldrow);
   if (rc) return rc;
   if (j > 0) {

@@ -15,12 +15,20 @@
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 16, STAGES = 6;
-constexpr int CONSUMER_WARPS = 16;
-constexpr int THREADS = (CONSUMER_WARPS + 1) * 32;
-constexpr int TILE_BYTES = BM * BK * 8;           // 16 KB per operand tile
-constexpr int STAGE_BYTES = 2 * TILE_BYTES;       // A + B
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int BK = 16, STAGES = 6;
+// TMA box = one operand tile: TILE rows x 16 doubles (each buffer carries a descriptor per tile size, TMap2)
+// Two tile sizes share one code path: 128 x 128 (16 consumer warps, 1 CTA / SM) for the bulk, 64 x 64 (4 consumer warps,
+// 2 CTAs / SM) for launches with too few 128-tiles to fill the GPU (panel chain, small matrices).  Per output element
+// both consume K in the same order, so results do not depend on the tile size.
+template <int TILE> struct Cfg {
+  static constexpr int WG = TILE / 32;                       // warp grid is WG x WG, each warp 32 x 32
+  static constexpr int CONSUMER_WARPS = WG * WG;
+  static constexpr int THREADS = (CONSUMER_WARPS + 1) * 32;
+  static constexpr int TILE_BYTES = TILE * BK * 8;           // one operand tile
+  static constexpr int STAGE_BYTES = 2 * TILE_BYTES;         // A + B
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int MIN_CTAS = TILE == 128 ? 1 : 2;
+};
 
 struct GemmParams {
   CUtensorMap mapA, mapB, mapAdiag, mapBdiag;
@@ -76,8 +84,12 @@ __device__ __forceinline__ double lds64(uint32_t addr) {
   return v;
 }
 
-__global__ void __launch_bounds__(THREADS, 1)
+template <int TILE>
+__global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS)
 gemm_nt_dmma_kernel(const __grid_constant__ GemmParams p) {
+  constexpr int BM = TILE, BN = TILE;
+  constexpr int CONSUMER_WARPS = Cfg<TILE>::CONSUMER_WARPS, WG = Cfg<TILE>::WG;
+  constexpr int TILE_BYTES = Cfg<TILE>::TILE_BYTES, STAGE_BYTES = Cfg<TILE>::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   // 1024B alignment for the 128B swizzle atom
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -158,8 +170,8 @@ gemm_nt_dmma_kernel(const __grid_constant__ GemmParams p) {
     return;
   }
 
-  // ===== consumers: 16 warps, 4 (m) x 4 (n), each 32 x 32 =====
-  const int wm = warp >> 2, wn = warp & 3;
+  // ===== consumers: WG x WG warps, each 32 x 32 =====
+  const int wm = warp / WG, wn = warp % WG;
   const int g = lane >> 2, t = lane & 3;
   double acc[4][4][2];
 #pragma unroll
@@ -252,7 +264,7 @@ PFN_encodeTiled g_encode = nullptr;
 
 }  // namespace
 
-int make_tensor_map(gpp_handle* h, CUtensorMap* map, const double* base, long rows, long cols, long ld) {
+int make_tensor_map(gpp_handle* h, TMap2* map, const double* base, long rows, long cols, long ld) {
   if (!g_encode) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -263,49 +275,64 @@ int make_tensor_map(gpp_handle* h, CUtensorMap* map, const double* base, long ro
   if ((reinterpret_cast<uintptr_t>(base) & 15) || ((ld * 8) & 15)) { h->err = "tensor map: base/stride not 16B aligned"; return -1; }
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t gstr[1] = {(cuuint64_t)ld * 8};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), gdim, gstr, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { h->err = "cuTensorMapEncodeTiled failed: " + std::to_string((int)r); return GPP_CUDA_ERR; }
+  for (int v = 0; v < 2; ++v) {
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)(v == 0 ? 128 : 64)};
+    CUresult r = g_encode(v == 0 ? &map->m128 : &map->m64, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), gdim, gstr,
+                          box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { h->err = "cuTensorMapEncodeTiled failed: " + std::to_string((int)r); return GPP_CUDA_ERR; }
+  }
   return GPP_OK;
 }
 
-int gemm_nt_launch(gpp_handle* h, const GemmDesc& d) {
-  if (d.bd_count <= 0 && (d.m <= 0 || d.n <= 0)) return GPP_OK;
+namespace {
+template <int TILE>
+int launch_tile(gpp_handle* h, const GemmDesc& d, GemmParams& p) {
+  auto pick = [](const TMap2* m) -> const CUtensorMap& { return TILE == 128 ? m->m128 : m->m64; };
+  p.mapA = pick(d.mapA);
+  p.mapB = pick(d.mapB);
+  p.mapAdiag = pick(d.mapAdiag ? d.mapAdiag : d.mapA);
+  p.mapBdiag = pick(d.mapBdiag ? d.mapBdiag : d.mapB);
   static bool attr_set = false;
   if (!attr_set) {
-    CUDA_TRY(h, cudaFuncSetAttribute(gemm_nt_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    CUDA_TRY(h, cudaFuncSetAttribute(gemm_nt_dmma_kernel<TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<TILE>::SMEM_BYTES));
     attr_set = true;
   }
+  p.tiles_m = (d.m + TILE - 1) / TILE;
+  p.tiles_n = (d.n + TILE - 1) / TILE;
+  long ntiles;
+  if (p.bd_mode) {
+    const int nt = d.bd_nb / TILE;
+    ntiles = (long)d.bd_count * (nt * (nt + 1) / 2);
+  } else if (d.lower_only) {
+    ntiles = (long)p.tiles_m * (p.tiles_m + 1) / 2;     // square lower-triangular tile set (a_row0 == b_row0, m == n)
+  } else {
+    ntiles = (long)p.tiles_m * p.tiles_n;
+  }
+  gemm_nt_dmma_kernel<TILE><<<(unsigned)ntiles, Cfg<TILE>::THREADS, Cfg<TILE>::SMEM_BYTES, h->cur>>>(p);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return GPP_OK;
+}
+}  // namespace
+
+int gemm_nt_launch(gpp_handle* h, const GemmDesc& d) {
+  if (d.bd_count <= 0 && (d.m <= 0 || d.n <= 0)) return GPP_OK;
   GemmParams p;
-  p.mapA = *d.mapA;
-  p.mapB = *d.mapB;
   p.has_adiag = d.mapAdiag != nullptr;
   p.has_bdiag = d.mapBdiag != nullptr;
-  p.mapAdiag = d.mapAdiag ? *d.mapAdiag : *d.mapA;
-  p.mapBdiag = d.mapBdiag ? *d.mapBdiag : *d.mapB;
   p.a_row0 = d.a_row0; p.b_row0 = d.b_row0;
   p.C = d.C; p.ldc = d.ldc; p.Cin = d.Cin; p.ldcin = d.ldcin;
   p.m = d.m; p.n = d.n; p.k0 = d.k0; p.k1 = d.k1; p.kb_off = d.kb_off; p.ktri = d.ktri;
   p.diag_nb = d.diag_nb > 0 ? d.diag_nb : (1 << 30);
   p.alpha = d.alpha; p.lower_only = d.lower_only;
-  p.tiles_m = (d.m + BM - 1) / BM;
-  p.tiles_n = (d.n + BN - 1) / BN;
   p.bd_mode = d.bd_count > 0; p.bd_world = d.bd_world; p.bd_rank = d.bd_rank; p.bd_lblk0 = d.bd_lblk0; p.bd_nb = d.bd_nb; p.bd_M = d.bd_M;
-  long ntiles;
-  if (p.bd_mode) {
-    const int nt = d.bd_nb / BM;
-    ntiles = (long)d.bd_count * (nt * (nt + 1) / 2);
-  } else if (d.lower_only) {
-    // square lower-triangular tile set (requires a_row0 == b_row0 and m == n)
-    ntiles = (long)p.tiles_m * (p.tiles_m + 1) / 2;
-  } else {
-    ntiles = (long)p.tiles_m * p.tiles_n;
-  }
-  gemm_nt_dmma_kernel<<<(unsigned)ntiles, THREADS, SMEM_BYTES, h->cur>>>(p);
-  h->launches++;
-  CUDA_TRY(h, cudaGetLastError());
-  return GPP_OK;
+  // tile choice: 64 x 64 when the 128-tiling would occupy less than half of the SMs
+  long t128;
+  if (p.bd_mode) { const int nt = d.bd_nb / 128; t128 = (long)d.bd_count * (nt * (nt + 1) / 2); }
+  else { const long tm = (d.m + 127) / 128, tn = (d.n + 127) / 128; t128 = d.lower_only ? tm * (tm + 1) / 2 : tm * tn; }
+  const int force = h->force_tile;
+  const bool small = force ? (force == 64) : (t128 < 74);
+  return small ? launch_tile<64>(h, d, p) : launch_tile<128>(h, d, p);
 }

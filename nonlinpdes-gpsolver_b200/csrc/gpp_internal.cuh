@@ -9,6 +9,11 @@
 #include <string>
 #include <vector>
 
+// TMA descriptors of one buffer for both GEMM tile sizes (box 16 x 128 and 16 x 64 doubles, 128B swizzle)
+struct TMap2 {
+  CUtensorMap m128, m64;
+};
+
 #define GPP_MAX_SLOTS 2      // Darcy needs Theta_u and Theta_a
 #define GPP_MAX_BLOCKS 4     // row-operator blocks per Gram matrix
 #define GPP_MAX_ZBLOCKS 6    // unknown blocks (Darcy: w0 w1 w2 v0 v1 v2)
@@ -52,7 +57,7 @@ struct GramSlot {
   double* Ainv = nullptr;                // Mint x ldA
   long ldA = 0;
   bool factored = false, inverted = false;
-  CUtensorMap mapT, mapUdiag;            // TMA descriptors (box 16 x 128 doubles, 128B swizzle)
+  TMap2 mapT, mapUdiag;            // TMA descriptors (box 16 x 128 doubles, 128B swizzle)
   double kp_b1 = 0, kp_b2 = 0;           // kernel scales b1, b2
   double kp_e1 = 0, kp_e2 = 0;           // exponent coefficients (see gram.cu)
   int kernel_id = 0;
@@ -79,7 +84,7 @@ struct GnState {
   long ldH = 0;
   double* g = nullptr;        // n
   double* scal = nullptr;     // small device scratch for reductions
-  CUtensorMap mapH;
+  TMap2 mapH;
   bool ready = false;
 };
 
@@ -91,6 +96,7 @@ struct gpp_handle {
   cudaStream_t sP = nullptr;          // look-ahead: high-priority stream of the panel chain
   std::vector<cudaEvent_t> evpool;    // events of the look-ahead dependency graph
   int lookahead = 1;
+  int force_tile = 0;                 // 0 = heuristic, 64 / 128 = force that GEMM tile size (tests, tuning)
   std::string err;
   int N = 0, Nb = 0;
   double* Xd = nullptr;       // N x 2
@@ -126,10 +132,10 @@ static inline long round_up(long x, long m) { return (x + m - 1) / m * m; }
 
 // ---- gemm_dmma.cu -----------------------------------------------------------
 struct GemmDesc {
-  const CUtensorMap* mapA;      // operand A rows (K-contiguous)
-  const CUtensorMap* mapB;      // operand B rows (K-contiguous)
-  const CUtensorMap* mapAdiag;  // optional clean diagonal blocks for A (U operand), else null
-  const CUtensorMap* mapBdiag;  // optional clean diagonal blocks for B
+  const TMap2* mapA;      // operand A rows (K-contiguous)
+  const TMap2* mapB;      // operand B rows (K-contiguous)
+  const TMap2* mapAdiag;  // optional clean diagonal blocks for A (U operand), else null
+  const TMap2* mapBdiag;  // optional clean diagonal blocks for B
   int a_row0, b_row0;           // first row of A / B operand (map coordinates)
   double* C; long ldc;          // output origin pointer (row-major), already offset
   const double* Cin; long ldcin;// optional addend (may alias C), already offset
@@ -145,13 +151,13 @@ struct GemmDesc {
   int bd_count, bd_world, bd_rank, bd_lblk0, bd_nb, bd_M;
 };
 int gemm_nt_launch(gpp_handle* h, const GemmDesc& d);
-int make_tensor_map(gpp_handle* h, CUtensorMap* map, const double* base, long rows, long cols, long ld);
+int make_tensor_map(gpp_handle* h, TMap2* map, const double* base, long rows, long cols, long ld);
 
 // ---- chol.cu ---------------------------------------------------------------
 struct Mat {
   double* base;
   long ld;
-  const CUtensorMap* map;
+  const TMap2* map;
 };
 // X * L^T = P in place; P = rows x nb block of P at (pr0, pc0); L = nb x nb lower block of L at (lr0, lc0)
 int trsm_right_lt(gpp_handle* h, const Mat& P, int pr0, int pc0, int rows, const Mat& L, int lr0, int lc0, int nb);
@@ -160,7 +166,7 @@ int potrf_diag(gpp_handle* h, const Mat& A, int r0, int c0, int nb, int gidx0);
 // ---- gram.cu: rows [i_begin, i_begin + nrows) of row-operator block `prow`, all column blocks q <= prow
 int gram_assemble_rows(gpp_handle* h, GramSlot& s, int prow, int i_begin, int nrows, double* dst, long ld);
 // Blocked lower Cholesky of the n x n matrix at A (row-major, ld), in place, using map for TMA.
-int potrf_lower(gpp_handle* h, double* A, long ld, int n, const CUtensorMap* map);
+int potrf_lower(gpp_handle* h, double* A, long ld, int n, const TMap2* map);
 // U = L^{-T} into the strict upper triangle + udiag, then Ainv = (L L^T)^{-1}[0:mint,0:mint]
 int inverse_interior(gpp_handle* h, GramSlot& s);
 // y = L^{-1} b (forward) / y = L^{-T} b (backward), vectors, in place in x
