@@ -48,6 +48,9 @@ long gpp_launch_count(gpp_handle* h);
 /* CUDA-event timer on the handle's stream */
 int gpp_timer_start(gpp_handle* h);
 int gpp_timer_stop(gpp_handle* h, float* ms);
+/* a second, independent event pair (outer timed region of bench.py around whole solves) */
+int gpp_timer2_start(gpp_handle* h);
+int gpp_timer2_stop(gpp_handle* h, float* ms);
 
 /* collocation points: X.sampled_pts / X.get_sampled_points  src/PDEs.py:34-54 */
 int gpp_set_points(gpp_handle* h, const double* X_domain, int N_domain, const double* X_boundary, int N_boundary);

@@ -33,6 +33,8 @@ def _sig(lib):
         "gpp_sync": [H],
         "gpp_timer_start": [H],
         "gpp_timer_stop": [H, C.POINTER(C.c_float)],
+        "gpp_timer2_start": [H],
+        "gpp_timer2_stop": [H, C.POINTER(C.c_float)],
         "gpp_set_points": [H, _dp, C.c_int, _dp, C.c_int],
         "gpp_gram_assemble": [H, C.c_int, C.c_int, C.c_int, _dp],
         "gpp_gram_size": [H, C.c_int, _ip, _ip],
@@ -165,6 +167,14 @@ class Engine:
     def timer_stop(self):
         ms = C.c_float()
         self._ck(self._lib.gpp_timer_stop(self._h, C.byref(ms)), "gpp_timer_stop")
+        return float(ms.value)
+
+    def timer2_start(self):
+        self._ck(self._lib.gpp_timer2_start(self._h), "gpp_timer2_start")
+
+    def timer2_stop(self):
+        ms = C.c_float()
+        self._ck(self._lib.gpp_timer2_stop(self._h, C.byref(ms)), "gpp_timer2_stop")
         return float(ms.value)
 
     # ---- points / Gram

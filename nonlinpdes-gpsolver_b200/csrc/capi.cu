@@ -152,6 +152,19 @@ int gpp_timer_stop(gpp_handle* h, float* ms) {
   return GPP_OK;
 }
 
+int gpp_timer2_start(gpp_handle* h) {
+  if (!h) return -1;
+  CUDA_TRY(h, cudaEventRecord(h->ev[8], h->stream));
+  return GPP_OK;
+}
+int gpp_timer2_stop(gpp_handle* h, float* ms) {
+  if (!h || !ms) return -1;
+  CUDA_TRY(h, cudaEventRecord(h->ev[9], h->stream));
+  CUDA_TRY(h, cudaEventSynchronize(h->ev[9]));
+  CUDA_TRY(h, cudaEventElapsedTime(ms, h->ev[8], h->ev[9]));
+  return GPP_OK;
+}
+
 int gpp_set_points(gpp_handle* h, const double* Xd, int N, const double* Xb, int Nb) {
   if (!h) return -1;
   if (!Xd || N <= 0) { h->err = "X_domain missing"; return -2; }

@@ -109,7 +109,7 @@ struct gpp_handle {
   size_t work_bytes = 0;
   int NB = 512;               // block-column width of the blocked factorisations
   // timing
-  cudaEvent_t ev[8];
+  cudaEvent_t ev[10];               // [0,1] phase timer, [2..7] GN trace, [8,9] outer (bench) timer
   float t_asm = 0, t_potrf = 0, t_inv = 0, t_step = 0;
   long launches = 0;
   // distributed (dist.cu)
