@@ -9,6 +9,8 @@
 // the vector triangular solves.
 #include "gpp_internal.cuh"
 
+#include <cstdlib>
+
 namespace {
 
 constexpr int BASE = 64;
@@ -325,30 +327,98 @@ int potrf_lower(gpp_handle* h, double* A, long ld, int n, const TMap2* map) {
 // clean diagonal blocks in udiag), then Ainv = (U U^T)[0:Mint, 0:Mint] = (Theta^{-1}) interior block.
 int inverse_interior(gpp_handle* h, GramSlot& s) {
   const int NB = h->NB, M = s.M;
+  static const bool trace = getenv("GPP_TRACE") != nullptr;
+  if (trace) cudaEventRecord(h->ev[2], h->stream);
   Mat T{s.T, s.ld, &s.mapT};
   Mat UD{s.udiag, (long)NB, &s.mapUdiag};
-  for (int o = 0; o < M; o += NB) {
+  const int nblk = (M + NB - 1) / NB;
+  // block column i of U:  T_i = -U[0:o, 0:o] L[i, 0:o]^T  (o = i NB; rows are upper triangular: ktri), then T_i L_ii^{-T}
+  auto col_gemm = [&](int i, int rows, int k0, int k1, bool accumulate) -> int {
+    const int o = i * NB;
     const int nbi = (M - o < NB) ? (M - o) : NB;
-    {
-      long tot = (long)NB * NB;
-      fill_identity_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->cur>>>(s.udiag + (long)o * NB, NB, NB, NB);
-      h->launches++;
-    }
-    int rc = trsm_right_lt(h, UD, o, 0, nbi, T, o, o, nbi);   // X L_ii^T = I
-    if (rc) return rc;
-    if (o > 0) {
-      GemmDesc d{};
-      d.mapA = &s.mapT; d.mapAdiag = &s.mapUdiag; d.mapB = &s.mapT; d.mapBdiag = nullptr;
-      d.a_row0 = 0; d.b_row0 = o;
-      d.C = s.T + o; d.ldc = s.ld; d.Cin = nullptr; d.ldcin = 0;
-      d.m = o; d.n = nbi; d.k0 = 0; d.k1 = o; d.kb_off = 0;
-      d.ktri = 1; d.diag_nb = NB; d.alpha = -1.0; d.lower_only = 0;
-      rc = gemm_nt_launch(h, d);
+    if (rows <= 0 || k1 <= k0) return GPP_OK;
+    GemmDesc d{};
+    d.mapA = &s.mapT; d.mapAdiag = &s.mapUdiag; d.mapB = &s.mapT; d.mapBdiag = nullptr;
+    d.a_row0 = 0; d.b_row0 = o;
+    d.C = s.T + o; d.ldc = s.ld;
+    d.Cin = accumulate ? d.C : nullptr; d.ldcin = s.ld;
+    d.m = rows; d.n = nbi; d.k0 = k0; d.k1 = k1; d.kb_off = 0;
+    d.ktri = 1; d.diag_nb = NB; d.alpha = -1.0; d.lower_only = 0;
+    return gemm_nt_launch(h, d);
+  };
+  auto diag_inverse = [&](int i) -> int {            // udiag block i = L_ii^{-T}  (X L_ii^T = I)
+    const int o = i * NB;
+    const int nbi = (M - o < NB) ? (M - o) : NB;
+    const long tot = (long)NB * NB;
+    fill_identity_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->cur>>>(s.udiag + (long)o * NB, NB, NB, NB);
+    h->launches++;
+    return trsm_right_lt(h, UD, o, 0, nbi, T, o, o, nbi);
+  };
+  const bool la = h->lookahead && nblk >= 4 && h->sP != nullptr;
+  if (!la) {
+    for (int i = 0; i < nblk; ++i) {
+      const int o = i * NB;
+      const int nbi = (M - o < NB) ? (M - o) : NB;
+      int rc = diag_inverse(i);
+      if (rc) return rc;
+      rc = col_gemm(i, o, 0, o, false);
       if (rc) return rc;
       rc = trsm_right_lt(h, T, 0, o, o, T, o, o, nbi);
       if (rc) return rc;
     }
+  } else {
+    // look-ahead, same schedule as potrf_lower: G1(i) = K < (i-1) NB on alternating streams (needs columns <= i-2),
+    // G2(i) = last K block + the solve against L_ii on the high-priority stream
+    size_t used = 0;
+    cudaEvent_t ev_start = next_event(h, used);
+    CUDA_TRY(h, cudaEventRecord(ev_start, h->stream));
+    for (int k = 0; k < 2; ++k) CUDA_TRY(h, cudaStreamWaitEvent(h->sG[k], ev_start, 0));
+    CUDA_TRY(h, cudaStreamWaitEvent(h->sP, ev_start, 0));
+    std::vector<cudaEvent_t> evP(nblk);
+    int rc = GPP_OK;
+    for (int i = 0; i < nblk && !rc; ++i) {
+      const int o = i * NB;
+      const int nbi = (M - o < NB) ? (M - o) : NB;
+      bool have_g1 = false;
+      if (i >= 2) {
+        cudaStream_t sg = h->sG[i & 1];
+        CUDA_TRY(h, cudaStreamWaitEvent(sg, evP[i - 2], 0));
+        h->cur = sg;
+        rc = col_gemm(i, o - NB, 0, o - NB, false);          // rows of blocks 0..i-2, K up to (i-1) NB
+        if (rc) break;
+        cudaEvent_t eg = next_event(h, used);
+        CUDA_TRY(h, cudaEventRecord(eg, sg));
+        CUDA_TRY(h, cudaStreamWaitEvent(h->sP, eg, 0));
+        have_g1 = true;
+      }
+      h->cur = h->sP;
+      rc = diag_inverse(i);
+      if (rc) break;
+      if (i >= 1) {
+        // rows of block i-1 start here (no G1 part): clear them so that one accumulating GEMM covers all rows
+        CUDA_TRY(h, cudaMemset2DAsync(s.T + (long)(o - NB) * s.ld + o, s.ld * 8, 0, (size_t)nbi * 8, NB, h->sP));
+        if (have_g1) {
+          rc = col_gemm(i, o, o - NB, o, true);
+        } else {
+          rc = col_gemm(i, o, 0, o, false);                  // i == 1: single GEMM
+        }
+        if (rc) break;
+        rc = trsm_right_lt(h, T, 0, o, o, T, o, o, nbi);
+        if (rc) break;
+      }
+      evP[i] = next_event(h, used);
+      CUDA_TRY(h, cudaEventRecord(evP[i], h->sP));
+    }
+    h->cur = h->stream;
+    if (rc) return rc;
+    CUDA_TRY(h, cudaStreamWaitEvent(h->stream, evP[nblk - 1], 0));
+    for (int k = 0; k < 2; ++k) {
+      cudaEvent_t e = next_event(h, used);
+      CUDA_TRY(h, cudaEventRecord(e, h->sG[k]));
+      CUDA_TRY(h, cudaStreamWaitEvent(h->stream, e, 0));
+    }
   }
+  if (trace) cudaEventRecord(h->ev[3], h->stream);
   {
     GemmDesc d{};
     d.mapA = &s.mapT; d.mapAdiag = &s.mapUdiag; d.mapB = &s.mapT; d.mapBdiag = &s.mapUdiag;
@@ -358,10 +428,18 @@ int inverse_interior(gpp_handle* h, GramSlot& s) {
     d.ktri = 1; d.diag_nb = NB; d.alpha = 1.0; d.lower_only = 1;
     int rc = gemm_nt_launch(h, d);
     if (rc) return rc;
+    if (trace) cudaEventRecord(h->ev[4], h->stream);
     dim3 grid((s.Mint + 31) / 32, (s.Mint + 31) / 32), blk(32, 8);
     symmetrize_kernel<<<grid, blk, 0, h->cur>>>(s.Ainv, s.ldA, s.Mint);
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
+  }
+  if (trace) {
+    cudaEventRecord(h->ev[5], h->stream);
+    cudaEventSynchronize(h->ev[5]);
+    float t[3];
+    for (int k = 0; k < 3; ++k) cudaEventElapsedTime(&t[k], h->ev[2 + k], h->ev[3 + k]);
+    fprintf(stderr, "[gpp trace] inverse: U = L^-T %.2f ms | U U^T %.2f | symmetrize %.2f\n", t[0], t[1], t[2]);
   }
   return GPP_OK;
 }
