@@ -30,10 +30,12 @@ sys.path.insert(0, ROOT)
 
 FP64_PEAK_FALLBACK_TFLOPS = 36.19   # cuBLAS DGEMM 8192^3 on this pool's B200 (profiles/r01_cublas_dgemm_cusolver_potrf.txt)
 HBM_PEAK_FALLBACK_GBS = 6650.0      # B200_PROFILING.md fallback
-# dram__bytes_read.sum + dram__bytes_write.sum of one large left-looking update launch (628 tiles, K=20480;
-# algorithmic operand bytes 3.70e9), from the ncu --set full capture profiles/r01_gemm_big_N20k.ncu-rep
-NCU_GEMM_TRAFFIC = {"bytes_per_launch": 3.715e9 + 0.098e9, "algorithmic_bytes_per_launch": 3.70e9,
-                    "launch": "gemm_nt_dmma_kernel 628 tiles K=20480 (N_domain=20000, block column 40)", "source": "profiles/r01_ncu_summary.md"}
+# dram__bytes_read.sum + dram__bytes_write.sum of one large left-looking update launch of THIS workload (N_domain=40000,
+# block column 100: 928 tiles, K=50688; algorithmic operand bytes: A rows 12.04e9 + B 0.21e9 + C read/write 0.24e9), from the
+# ncu --set full capture profiles/r01_gemm_big_N40k.ncu-rep (48.2 ms, DMMA pipe 96 % of active cycles)
+NCU_GEMM_TRAFFIC = {"bytes_per_launch": 13.385e9 + 0.138e9, "algorithmic_bytes_per_launch": 12.49e9,
+                    "launch": "gemm_nt_dmma_kernel<128> 928 tiles K=50688 (N_domain=40000, block column 100)",
+                    "source": "profiles/r01_ncu_summary.md"}
 
 
 def u_true(x1, x2):
