@@ -90,6 +90,7 @@ int gpp_create(int device, gpp_handle** out) {
 }
 
 int gpp_destroy(gpp_handle* h) {
+  if (h) cudaSetDevice(h->device);
   if (!h) return -1;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
@@ -113,6 +114,7 @@ int gpp_destroy(gpp_handle* h) {
 const char* gpp_last_error(gpp_handle* h) { return h ? h->err.c_str() : "null handle"; }
 
 int gpp_set_option(gpp_handle* h, const char* name, double value) {
+  if (h) cudaSetDevice(h->device);
   if (!h || !name) return -1;
   if (!strcmp(name, "NB")) {
     int nb = (int)value;
@@ -132,6 +134,7 @@ int gpp_set_option(gpp_handle* h, const char* name, double value) {
 }
 
 int gpp_sync(gpp_handle* h) {
+  if (h) cudaSetDevice(h->device);
   if (!h) return -1;
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   return GPP_OK;
@@ -140,11 +143,13 @@ int gpp_sync(gpp_handle* h) {
 long gpp_launch_count(gpp_handle* h) { return h ? h->launches : -1; }
 
 int gpp_timer_start(gpp_handle* h) {
+  if (h) cudaSetDevice(h->device);
   if (!h) return -1;
   CUDA_TRY(h, cudaEventRecord(h->ev[0], h->stream));
   return GPP_OK;
 }
 int gpp_timer_stop(gpp_handle* h, float* ms) {
+  if (h) cudaSetDevice(h->device);
   if (!h || !ms) return -1;
   CUDA_TRY(h, cudaEventRecord(h->ev[1], h->stream));
   CUDA_TRY(h, cudaEventSynchronize(h->ev[1]));
@@ -153,11 +158,13 @@ int gpp_timer_stop(gpp_handle* h, float* ms) {
 }
 
 int gpp_timer2_start(gpp_handle* h) {
+  if (h) cudaSetDevice(h->device);
   if (!h) return -1;
   CUDA_TRY(h, cudaEventRecord(h->ev[8], h->stream));
   return GPP_OK;
 }
 int gpp_timer2_stop(gpp_handle* h, float* ms) {
+  if (h) cudaSetDevice(h->device);
   if (!h || !ms) return -1;
   CUDA_TRY(h, cudaEventRecord(h->ev[9], h->stream));
   CUDA_TRY(h, cudaEventSynchronize(h->ev[9]));
@@ -166,6 +173,7 @@ int gpp_timer2_stop(gpp_handle* h, float* ms) {
 }
 
 int gpp_set_points(gpp_handle* h, const double* Xd, int N, const double* Xb, int Nb) {
+  if (h) cudaSetDevice(h->device);
   if (!h) return -1;
   if (!Xd || N <= 0) { h->err = "X_domain missing"; return -2; }
   if (Nb < 0 || (Nb > 0 && !Xb)) { h->err = "X_boundary missing"; return -4; }
@@ -182,6 +190,7 @@ int gpp_set_points(gpp_handle* h, const double* Xd, int N, const double* Xb, int
 }
 
 int gpp_gram_assemble(gpp_handle* h, int slot, int layout, int kernel, const double* kparams) {
+  if (h) cudaSetDevice(h->device);
   if (bad_slot(h, slot, false)) return -2;
   if (!h->Xall) { h->err = "points not set"; return -1; }
   if (layout < 0 || layout > 3) { h->err = "bad layout"; return -3; }
@@ -213,6 +222,7 @@ int gpp_gram_assemble(gpp_handle* h, int slot, int layout, int kernel, const dou
 }
 
 int gpp_gram_size(gpp_handle* h, int slot, int* M, int* Mint) {
+  if (h) cudaSetDevice(h->device);
   if (bad_slot(h, slot)) return -2;
   if (M) *M = h->slot[slot].M;
   if (Mint) *Mint = h->slot[slot].Mint;
@@ -220,6 +230,7 @@ int gpp_gram_size(gpp_handle* h, int slot, int* M, int* Mint) {
 }
 
 int gpp_gram_get_diag(gpp_handle* h, int slot, double* out) {
+  if (h) cudaSetDevice(h->device);
   if (bad_slot(h, slot)) return -2;
   if (!out) return -3;
   GramSlot& s = h->slot[slot];
@@ -233,6 +244,7 @@ int gpp_gram_get_diag(gpp_handle* h, int slot, double* out) {
 }
 
 int gpp_gram_add_diag(gpp_handle* h, int slot, const double* add) {
+  if (h) cudaSetDevice(h->device);
   if (bad_slot(h, slot)) return -2;
   if (!add) return -3;
   GramSlot& s = h->slot[slot];
@@ -246,6 +258,7 @@ int gpp_gram_add_diag(gpp_handle* h, int slot, const double* add) {
 }
 
 int gpp_gram_download(gpp_handle* h, int slot, int what, double* out) {
+  if (h) cudaSetDevice(h->device);
   if (bad_slot(h, slot)) return -2;
   if (!out || what < 0 || what > 2) return -3;
   GramSlot& s = h->slot[slot];
@@ -268,6 +281,7 @@ int gpp_gram_download(gpp_handle* h, int slot, int what, double* out) {
 }
 
 int gpp_gram_upload(gpp_handle* h, int slot, const double* theta) {
+  if (h) cudaSetDevice(h->device);
   if (bad_slot(h, slot)) return -2;
   if (!theta) return -3;
   GramSlot& s = h->slot[slot];
@@ -286,6 +300,7 @@ int gpp_gram_upload(gpp_handle* h, int slot, const double* theta) {
 }
 
 int gpp_potrf(gpp_handle* h, int slot, int* info) {
+  if (h) cudaSetDevice(h->device);
   if (bad_slot(h, slot)) return -2;
   CUDA_TRY(h, cudaSetDevice(h->device));
   GramSlot& s = h->slot[slot];
@@ -302,6 +317,7 @@ int gpp_potrf(gpp_handle* h, int slot, int* info) {
 }
 
 int gpp_inverse(gpp_handle* h, int slot) {
+  if (h) cudaSetDevice(h->device);
   if (bad_slot(h, slot)) return -2;
   CUDA_TRY(h, cudaSetDevice(h->device));
   GramSlot& s = h->slot[slot];
@@ -324,6 +340,7 @@ int gpp_inverse(gpp_handle* h, int slot) {
 }
 
 int gpp_solve_vec(gpp_handle* h, int slot, const double* b, double* x) {
+  if (h) cudaSetDevice(h->device);
   if (bad_slot(h, slot)) return -2;
   if (!b || !x) return -3;
   GramSlot& s = h->slot[slot];
@@ -342,6 +359,7 @@ int gpp_solve_vec(gpp_handle* h, int slot, const double* b, double* x) {
 
 int gpp_gn_setup(gpp_handle* h, int pde, const double* params, const double* rhs_f, const double* bdy_g,
                  const double* data_u, int N_data, double noise) {
+  if (h) cudaSetDevice(h->device);
   if (!h) return -1;
   if (pde < 0 || pde > 4) { h->err = "bad pde"; return -2; }
   if (!rhs_f || (h->Nb > 0 && !bdy_g)) { h->err = "rhs_f / bdy_g missing"; return -4; }
@@ -405,6 +423,7 @@ int gpp_gn_setup(gpp_handle* h, int pde, const double* params, const double* rhs
 }
 
 int gpp_gn_set_z(gpp_handle* h, const double* z) {
+  if (h) cudaSetDevice(h->device);
   if (!h || !h->gn.ready) return -1;
   if (!z) return -2;
   CUDA_TRY(h, cudaMemcpyAsync(h->gn.z, z, sizeof(double) * h->gn.n, cudaMemcpyHostToDevice, h->stream));
@@ -413,6 +432,7 @@ int gpp_gn_set_z(gpp_handle* h, const double* z) {
 }
 
 int gpp_gn_get_z(gpp_handle* h, double* z) {
+  if (h) cudaSetDevice(h->device);
   if (!h || !h->gn.ready) return -1;
   if (!z) return -2;
   CUDA_TRY(h, cudaMemcpyAsync(z, h->gn.z, sizeof(double) * h->gn.n, cudaMemcpyDeviceToHost, h->stream));
@@ -432,6 +452,7 @@ static int gn_check(gpp_handle* h, bool need_inverse) {
 }
 
 int gpp_gn_loss(gpp_handle* h, double* loss) {
+  if (h) cudaSetDevice(h->device);
   int rc = gn_check(h, false);
   if (rc) return rc;
   if (!loss) return -4;
@@ -440,6 +461,7 @@ int gpp_gn_loss(gpp_handle* h, double* loss) {
 }
 
 int gpp_gn_step(gpp_handle* h, double step, double* loss) {
+  if (h) cudaSetDevice(h->device);
   int rc = gn_check(h, true);
   if (rc) return rc;
   if (!loss) return -4;
@@ -448,6 +470,7 @@ int gpp_gn_step(gpp_handle* h, double step, double* loss) {
 }
 
 int gpp_gn_grad_hess(gpp_handle* h, double* grad_out, double* hess_out) {
+  if (h) cudaSetDevice(h->device);
   int rc = gn_check(h, true);
   if (rc) return rc;
   CUDA_TRY(h, cudaSetDevice(h->device));
@@ -465,6 +488,7 @@ int gpp_gn_grad_hess(gpp_handle* h, double* grad_out, double* hess_out) {
 }
 
 int gpp_gn_residual(gpp_handle* h, int slot, double* F_out) {
+  if (h) cudaSetDevice(h->device);
   if (!h || !h->gn.ready) return -1;
   if (bad_slot(h, slot)) return -2;
   if (!F_out) return -3;
@@ -477,6 +501,7 @@ int gpp_gn_residual(gpp_handle* h, int slot, double* F_out) {
 }
 
 int gpp_gn_coef(gpp_handle* h, int slot, int p, int q, double* c_out, int* present) {
+  if (h) cudaSetDevice(h->device);
   if (!h || !h->gn.ready) return -1;
   if (slot < 0 || slot >= GPP_MAX_SLOTS || p < 0 || p >= GPP_MAX_BLOCKS || q < 0 || q >= GPP_MAX_ZBLOCKS) return -2;
   if (!c_out) return -3;
@@ -494,6 +519,7 @@ int gpp_gn_coef(gpp_handle* h, int slot, int p, int q, double* c_out, int* prese
 }
 
 int gpp_predict(gpp_handle* h, int slot, const double* Xtest, int ntest, const double* w, double* out) {
+  if (h) cudaSetDevice(h->device);
   if (bad_slot(h, slot)) return -2;
   if (!Xtest || ntest <= 0 || !w || !out) return -3;
   CUDA_TRY(h, cudaSetDevice(h->device));
@@ -511,6 +537,7 @@ int gpp_predict(gpp_handle* h, int slot, const double* Xtest, int ntest, const d
 }
 
 int gpp_theta_test(gpp_handle* h, int slot, const double* Xtest, int ntest, double* out) {
+  if (h) cudaSetDevice(h->device);
   if (bad_slot(h, slot)) return -2;
   if (!Xtest || ntest <= 0 || !out) return -3;
   CUDA_TRY(h, cudaSetDevice(h->device));
@@ -530,6 +557,7 @@ int gpp_theta_test(gpp_handle* h, int slot, const double* Xtest, int ntest, doub
 
 int gpp_kernel_eval(gpp_handle* h, int kernel, const double* kparams, int op_x, int op_y, const double* x1,
                     const double* x2, const double* y1, const double* y2, long n, double* out) {
+  if (h) cudaSetDevice(h->device);
   if (!h) return -1;
   if (kernel < 0 || kernel > 1 || !kparams) return -2;
   if (op_x < 0 || op_x > 4 || op_y < 0 || op_y > 4) { h->err = "bad operator id"; return -4; }

@@ -186,11 +186,11 @@ trsv_bwd_update_kernel(const double* __restrict__ Lrows, long ld, int cols, int 
 int trsm_right_lt(gpp_handle* h, const Mat& P, int pr0, int pc0, int rows, const Mat& L, int lr0, int lc0, int nb) {
   if (rows <= 0 || nb <= 0) return GPP_OK;
   if (nb <= BASE) {
-    static bool attr = false;
+    static bool attr[64] = {false};        // function attributes are per device
     const int smem = (BASE * LDS_PAD + TRSM_ROWS * LDS_PAD) * 8;
-    if (!attr) {
+    if (h->device >= 64 || !attr[h->device]) {
       CUDA_TRY(h, cudaFuncSetAttribute(trsm_base_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      attr = true;
+      if (h->device < 64) attr[h->device] = true;
     }
     trsm_base_kernel<<<(rows + TRSM_ROWS - 1) / TRSM_ROWS, TRSM_ROWS, smem, h->cur>>>(
         P.base + (long)pr0 * P.ld + pc0, P.ld, rows, L.base + (long)lr0 * L.ld + lc0, L.ld, nb);

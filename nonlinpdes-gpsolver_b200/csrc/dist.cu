@@ -72,6 +72,7 @@ int gpp_dist_unique_id(unsigned char* id128) {
 }
 
 int gpp_dist_init(gpp_handle* h, int rank, int world, const unsigned char* id128) {
+  if (h) cudaSetDevice(h->device);
   if (!h || !id128) return -1;
   if (world < 1 || rank < 0 || rank >= world) { h->err = "bad rank/world"; return -2; }
   if (h->dist) { h->err = "already initialised"; return -3; }
@@ -86,6 +87,7 @@ int gpp_dist_init(gpp_handle* h, int rank, int world, const unsigned char* id128
 }
 
 int gpp_dist_finalize(gpp_handle* h) {
+  if (h) cudaSetDevice(h->device);
   if (!h || !h->dist) return -1;
   DistState* d = ds(h);
   cudaStreamSynchronize(h->stream);
@@ -101,6 +103,7 @@ int gpp_dist_finalize(gpp_handle* h) {
 
 // Row-sharded Gram_matrix_assembly (src/Gram_matrice.py:11-187): this rank's block rows of Theta.
 int gpp_dist_gram_assemble(gpp_handle* h, int layout, int kernel, const double* kparams) {
+  if (h) cudaSetDevice(h->device);
   if (!h || !h->dist) return -1;
   if (!h->Xall) { h->err = "points not set"; return -1; }
   if (layout < 0 || layout > 3 || kernel < 0 || kernel > 1 || !kparams) return -2;
@@ -152,6 +155,7 @@ int gpp_dist_gram_assemble(gpp_handle* h, int layout, int kernel, const double* 
 }
 
 int gpp_dist_local_rows(gpp_handle* h, int* nloc, int* M) {
+  if (h) cudaSetDevice(h->device);
   if (!h || !h->dist) return -1;
   if (nloc) *nloc = ds(h)->nloc;
   if (M) *M = ds(h)->M;
@@ -160,6 +164,7 @@ int gpp_dist_local_rows(gpp_handle* h, int* nloc, int* M) {
 
 // diag_out[M]: the full diagonal on every rank (sum all-reduce of the owned parts)
 int gpp_dist_get_diag(gpp_handle* h, double* diag_out) {
+  if (h) cudaSetDevice(h->device);
   if (!h || !h->dist || !diag_out) return -1;
   DistState* d = ds(h);
   const int NB = h->NB, P = d->world, M = d->M;
@@ -176,6 +181,7 @@ int gpp_dist_get_diag(gpp_handle* h, double* diag_out) {
 }
 
 int gpp_dist_add_diag(gpp_handle* h, const double* add) {
+  if (h) cudaSetDevice(h->device);
   if (!h || !h->dist || !add) return -1;
   DistState* d = ds(h);
   const int NB = h->NB, P = d->world, M = d->M;
@@ -245,6 +251,7 @@ static int dist_factor_and_pack(gpp_handle* h, DistState* d, int j, double* rowb
 // column j on the main stream.  Two row buffers alternate; events order bulk(j) after bcast(j) and bcast(j+2) after
 // bulk(j).  NCCL calls are issued in the same order (j = 0, 1, ...) on the side stream of every rank.
 int gpp_dist_potrf(gpp_handle* h, int* info) {
+  if (h) cudaSetDevice(h->device);
   if (!h || !h->dist) return -1;
   DistState* d = ds(h);
   if (!d->Tloc) { h->err = "assemble first"; return -2; }
@@ -342,6 +349,7 @@ int gpp_dist_potrf(gpp_handle* h, int* info) {
 
 // out: nloc x M dense rows of this rank (lower triangle of Theta / L; entries above the diagonal are zeroed)
 int gpp_dist_download_local(gpp_handle* h, double* out) {
+  if (h) cudaSetDevice(h->device);
   if (!h || !h->dist || !out) return -1;
   DistState* d = ds(h);
   const int NB = h->NB, P = d->world, M = d->M;

@@ -294,10 +294,10 @@ int launch_tile(gpp_handle* h, const GemmDesc& d, GemmParams& p) {
   p.mapB = pick(d.mapB);
   p.mapAdiag = pick(d.mapAdiag ? d.mapAdiag : d.mapA);
   p.mapBdiag = pick(d.mapBdiag ? d.mapBdiag : d.mapB);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {false};      // function attributes are per device
+  if (h->device >= 64 || !attr_set[h->device]) {
     CUDA_TRY(h, cudaFuncSetAttribute(gemm_nt_dmma_kernel<TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<TILE>::SMEM_BYTES));
-    attr_set = true;
+    if (h->device < 64) attr_set[h->device] = true;
   }
   p.tiles_m = (d.m + TILE - 1) / TILE;
   p.tiles_n = (d.n + TILE - 1) / TILE;
