@@ -419,6 +419,7 @@ int gpp_gn_setup(gpp_handle* h, int pde, const double* params, const double* rhs
   CUDA_TRY(h, cudaMemsetAsync(g.z, 0, sizeof(double) * g.n, h->stream));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   g.ready = true;
+  g.current = false;
   return GPP_OK;
 }
 
@@ -428,6 +429,7 @@ int gpp_gn_set_z(gpp_handle* h, const double* z) {
   if (!z) return -2;
   CUDA_TRY(h, cudaMemcpyAsync(h->gn.z, z, sizeof(double) * h->gn.n, cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  h->gn.current = false;
   return GPP_OK;
 }
 
@@ -505,6 +507,7 @@ int gpp_gn_coef(gpp_handle* h, int slot, int p, int q, double* c_out, int* prese
   if (!h || !h->gn.ready) return -1;
   if (slot < 0 || slot >= GPP_MAX_SLOTS || p < 0 || p >= GPP_MAX_BLOCKS || q < 0 || q >= GPP_MAX_ZBLOCKS) return -2;
   if (!c_out) return -3;
+  h->gn.current = false;
   CUDA_TRY(h, cudaMemsetAsync(h->gn.coef, 0, sizeof(double) * GPP_MAX_SLOTS * GPP_MAX_BLOCKS * GPP_MAX_ZBLOCKS * (size_t)h->N, h->stream));
   int rc = gn_eval_F(h, h->gn.z, true);
   if (rc) return rc;

@@ -334,6 +334,7 @@ int gn_loss(gpp_handle* h, const double* d_z, double* loss_host) {
   if (rc) return rc;
   CUDA_TRY(h, cudaMemcpyAsync(loss_host, h->gn.scal, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  if (d_z == h->gn.z) h->gn.current = true;
   return GPP_OK;
 }
 
@@ -409,6 +410,11 @@ int gn_step(gpp_handle* h, double step, double* loss_host) {
   int rc;
   static const bool trace = getenv("GPP_TRACE") != nullptr;
   auto mark = [&](int k) { if (trace) cudaEventRecord(h->ev[2 + k], h->stream); };
+  if (!g.current) {            // z was replaced since the last loss evaluation: refresh F, s and the coefficients
+    double dummy;
+    rc = gn_loss(h, g.z, &dummy);
+    if (rc) return rc;
+  }
   mark(0);
   mark(1);
   rc = gn_grad_hess(h);
@@ -425,6 +431,7 @@ int gn_step(gpp_handle* h, double step, double* loss_host) {
   axpy_kernel<<<(g.n + 255) / 256, 256, 0, h->stream>>>(g.z, g.g, step, g.n);
   h->launches++;
   CUDA_TRY(h, cudaGetLastError());
+  g.current = false;
   mark(4);
   rc = gn_loss(h, g.z, loss_host);
   if (trace && !rc) {

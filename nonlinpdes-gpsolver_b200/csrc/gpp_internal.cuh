@@ -86,6 +86,7 @@ struct GnState {
   double* scal = nullptr;     // small device scratch for reductions
   TMap2 mapH;
   bool ready = false;
+  bool current = false;       // F, s = L^{-1} F and the coefficient vectors belong to the present z
 };
 
 struct gpp_handle {

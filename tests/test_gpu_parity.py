@@ -352,3 +352,57 @@ def test_grad_and_hessian_match_oracle(pkg):
         assert np.max(np.abs(g - gr)) <= 1e-6 * np.max(np.abs(gr))
         assert np.max(np.abs(H - Hr)) <= 1e-6 * np.max(np.abs(Hr))
         np.testing.assert_allclose(p.loss(z), ref.loss(z), rtol=1e-8)
+
+
+def test_midsize_factor_and_inverse_properties(pkg):
+    """Size-independent properties on a real (ill-conditioned) Gram matrix at N_domain=4000 (M=8260, 17 block columns:
+    look-ahead schedule, both GEMM tile sizes): L L^T reproduces Theta, and the interior inverse block satisfies
+    Theta[:, I] A[:, c] = e_c on sampled columns."""
+    np.random.seed(8)
+    N, Nb = 4000, 260
+    p = pkg["PDEs"].Nonlinear_elliptic2d(alpha=1.0, m=3, bdy=o.elliptic_u, rhs=o.elliptic_f)
+    p.sampled_pts(N, Nb)
+    p.Gram_matrix("Gaussian", 0.2, 1e-8, "adaptive")
+    M = 2 * N + p.N_boundary
+    np.testing.assert_allclose(p.ratio, N * 8 * (1 / 0.2 ** 2) ** 2 / (N + p.N_boundary), rtol=1e-13)   # analytic trace ratio
+    Theta = p.Theta
+    assert np.array_equal(Theta, Theta.T)
+    p.Gram_Cholesky()
+    assert p.chol_info == 0
+    L = p.L
+    R = L @ L.T - Theta
+    assert np.max(np.abs(R)) <= 1e-13 * np.max(np.abs(Theta)) * np.sqrt(M)
+    eng = p._engine()
+    eng.inverse(0)
+    A = eng.gram_download(0, 2)
+    assert A.shape == (2 * N, 2 * N) and np.array_equal(A, A.T)
+    # (Theta^{-1})[I, c] for a few interior columns c, from the device factor by two triangular solves
+    cols = [0, 1234, N - 1, N, 2 * N - 1]
+    for c in cols:
+        e = np.zeros(M); e[c] = 1.0
+        x = eng.solve_vec(0, e)
+        assert np.max(np.abs(A[:, c] - x[:2 * N])) <= 1e-6 * np.max(np.abs(x))
+
+
+def test_full_size_solve_properties(pkg):
+    """BASELINE configs[4] at full size (N_domain=40000, M=80804; no oracle at this size): the factorisation succeeds at
+    the bench nugget, the trace ratio is the analytic one, the loss decreases, and the solution reaches the accuracy
+    of the manufactured problem."""
+    import math
+    np.random.seed(0)
+    N = 40000
+    Nb = 4 * (math.ceil(math.sqrt(N)) + 1)
+    p = pkg["PDEs"].Nonlinear_elliptic2d(alpha=1.0, m=3, bdy=o.elliptic_u, rhs=o.elliptic_f)
+    p.sampled_pts(N, Nb)
+    init = np.random.normal(0.0, 1.0, N)
+    p.Gram_matrix("Gaussian", 0.2, 1e-12, "adaptive")
+    np.testing.assert_allclose(p.ratio, N * 8 * (1 / 0.2 ** 2) ** 2 / (N + p.N_boundary), rtol=1e-12)
+    p.Gram_Cholesky()
+    assert p.chol_info == 0
+    p.GN_method(4, 1, init, print_hist=False)
+    assert all(np.isfinite(p.loss_hist)) and all(b < a for a, b in zip(p.loss_hist, p.loss_hist[1:]))
+    err = np.abs(o.elliptic_u(p.X_domain[:, 0], p.X_domain[:, 1]) - p.sol_sampled_pts)
+    assert np.sqrt(np.mean(err ** 2)) < 1e-6 and err.max() < 1e-5
+    Xt = np.random.uniform(0, 1, (500, 2))
+    p.extend_sol(Xt)
+    assert np.max(np.abs(p.extended_sol - o.elliptic_u(Xt[:, 0], Xt[:, 1]))) < 1e-4
