@@ -6,29 +6,8 @@ from scipy.interpolate import griddata
 from scipy.sparse import diags
 from scipy.sparse.linalg import spsolve
 
-from _common import str2bool
+from _common import make_parser, unit_grid
 from nonlinpdes_gpsolver_b200.solver import solver_GP
-
-
-def get_parser():
-    parser = argparse.ArgumentParser(description='Darcy flow inverse problem GP solver')
-    parser.add_argument("--kernel", type=str, default="Gaussian")
-    parser.add_argument("--kernel_parameter", type=float, default=0.2)
-    parser.add_argument("--nugget", type=float, default=1e-8)
-    parser.add_argument("--nugget_type", type=str, default="adaptive", choices=["adaptive", "identity", 'none'])
-    parser.add_argument("--sampled_type", type=str, default='random', choices=['random', 'grid'])
-    parser.add_argument("--N_domain", type=int, default=400)
-    parser.add_argument("--N_boundary", type=int, default=100)
-    parser.add_argument("--N_data", type=int, default=60)
-    parser.add_argument("--noise_level", type=float, default=1e-3)
-    parser.add_argument("--method", type=str, default='elimination')
-    parser.add_argument("--initial_sol", type=str, default='rdm')
-    parser.add_argument("--GNsteps", type=int, default=8)
-    parser.add_argument("--step_size", type=int, default=1)
-    parser.add_argument("--print_hist", type=str2bool, default=True)
-    parser.add_argument("--show_figure", type=str2bool, default=False)
-    parser.add_argument("--randomseed", type=int, default=9999)
-    return parser.parse_args()
 
 
 def a(x1, x2):
@@ -52,20 +31,20 @@ def FD_Darcy_flow_2d(N, fun_a, f_val):
     return out
 
 
-cfg = get_parser()
+cfg = make_parser('Darcy flow inverse problem GP solver',
+                  [("--N_data", dict(type=int, default=60)), ("--noise_level", dict(type=float, default=1e-3))],
+                  nugget=1e-8, N_domain=400, N_boundary=100, randomseed=9999).parse_args()
 onp.random.seed(cfg.randomseed)
 print(f"[Seeds] random seeds: {cfg.randomseed}")
 solver = solver_GP(cfg, PDE_type="Darcy_flow2d")
 solver.set_equation(bdy=lambda x1, x2: 0, rhs=lambda x1, x2: 1, domain=onp.array([[0, 1], [0, 1]]))
 solver.auto_sample_IP(cfg.N_domain, cfg.N_boundary, cfg.N_data, sampled_type=cfg.sampled_type)
 N_pts_per_dim = 80
-xx = onp.linspace(0, 1, N_pts_per_dim)
-XX, YY = onp.meshgrid(xx, xx)
+XX, YY, X_test = unit_grid(N_pts_per_dim)
 u_truth_grid = FD_Darcy_flow_2d(N_pts_per_dim - 2, a, 1.0)
 data_u = griddata((XX.flatten(), YY.flatten()), u_truth_grid.reshape(-1), (solver.eqn.X_data[:, 0], solver.eqn.X_data[:, 1]), method='linear')
 solver.get_observed_data(data_u, cfg.noise_level)
 solver.solve()
-X_test = onp.concatenate((XX.reshape(-1, 1), YY.reshape(-1, 1)), axis=1)
 solver.test(X_test)
 test_u = onp.reshape(solver.eqn.extended_sol_u, (N_pts_per_dim, N_pts_per_dim))
 test_a = onp.reshape(solver.eqn.extended_sol_a, (N_pts_per_dim, N_pts_per_dim))

@@ -6,28 +6,8 @@ import scipy.sparse
 from scipy.sparse import diags, identity
 from scipy.sparse.linalg import spsolve
 
-from _common import str2bool
+from _common import make_parser, unit_grid
 from nonlinpdes_gpsolver_b200.solver import solver_GP
-
-
-def get_parser():
-    parser = argparse.ArgumentParser(description='Eikonal equation GP solver')
-    parser.add_argument("--eps", type=float, default=1e-1)
-    parser.add_argument("--kernel", type=str, default="Gaussian")
-    parser.add_argument("--kernel_parameter", type=float, default=0.2)
-    parser.add_argument("--nugget", type=float, default=1e-5)
-    parser.add_argument("--nugget_type", type=str, default="adaptive", choices=["adaptive", "identity", 'none'])
-    parser.add_argument("--sampled_type", type=str, default='random', choices=['random', 'grid'])
-    parser.add_argument("--N_domain", type=int, default=1000)
-    parser.add_argument("--N_boundary", type=int, default=200)
-    parser.add_argument("--method", type=str, default='elimination')
-    parser.add_argument("--initial_sol", type=str, default='zero')
-    parser.add_argument("--GNsteps", type=int, default=8)
-    parser.add_argument("--step_size", type=int, default=1)
-    parser.add_argument("--print_hist", type=str2bool, default=True)
-    parser.add_argument("--show_figure", type=str2bool, default=False)
-    parser.add_argument("--randomseed", type=int, default=None)
-    return parser.parse_args()
 
 
 def solve_Eikonal(N, epsilon):
@@ -47,7 +27,7 @@ def solve_Eikonal(N, epsilon):
     return XX, YY, onp.reshape(-epsilon * onp.log(sol_v), (N, N))
 
 
-cfg = get_parser()
+cfg = make_parser('Eikonal equation GP solver', [("--eps", dict(type=float, default=1e-1))], initial_sol="zero").parse_args()
 if cfg.randomseed is not None:
     onp.random.seed(cfg.randomseed)
 solver = solver_GP(cfg, PDE_type="Eikonal")
@@ -55,9 +35,7 @@ solver.set_equation(bdy=lambda x1, x2: 0, rhs=lambda x1, x2: 1, domain=onp.array
 solver.auto_sample(cfg.N_domain, cfg.N_boundary, sampled_type=cfg.sampled_type)
 solver.solve()
 N_pts = 60
-xx = onp.linspace(0, 1, N_pts)[1:-1]
-XX, YY = onp.meshgrid(xx, xx)
-X_test = onp.concatenate((XX.reshape(-1, 1), YY.reshape(-1, 1)), axis=1)
+XX, YY, X_test = unit_grid(N_pts, trim=True)
 solver.test(X_test)
 XX, YY, test_truth = solve_Eikonal(N_pts - 2, cfg.eps)
 solver.get_test_error(test_truth.flatten())

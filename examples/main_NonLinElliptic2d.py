@@ -5,33 +5,12 @@ import argparse
 
 import numpy as onp
 
-from _common import str2bool
+from _common import make_parser, unit_grid
 from nonlinpdes_gpsolver_b200.solver import solver_GP
 
-
-def get_parser():
-    parser = argparse.ArgumentParser(description='NonLinElliptic equation GP solver')
-    parser.add_argument("--alpha", type=float, default=1.0)
-    parser.add_argument("--m", type=float, default=3.0)
-    parser.add_argument("--kernel", type=str, default='Gaussian')
-    parser.add_argument("--kernel_parameter", type=float, default=0.2)
-    parser.add_argument("--nugget", type=float, default=1e-13)
-    parser.add_argument("--nugget_type", type=str, default="adaptive", choices=["adaptive", "identity", 'none'])
-    parser.add_argument("--sampled_type", type=str, default='random', choices=['random', 'grid'])
-    parser.add_argument("--N_domain", type=int, default=900)
-    parser.add_argument("--N_boundary", type=int, default=124)
-    parser.add_argument("--method", type=str, default='elimination', choices=['elimination', 'relaxation'])
-    parser.add_argument("--pen_lambda", type=float, default=1e-10)
-    parser.add_argument("--initial_sol", type=str, default='rdm')
-    parser.add_argument("--GNsteps", type=int, default=4)
-    parser.add_argument("--step_size", type=int, default=1)
-    parser.add_argument("--print_hist", type=str2bool, default=True)
-    parser.add_argument("--show_figure", type=str2bool, default=False)
-    parser.add_argument("--randomseed", type=int, default=None, help="numpy seed (the reference driver never seeds)")
-    return parser.parse_args()
-
-
-cfg = get_parser()
+cfg = make_parser('NonLinElliptic equation GP solver',
+                  [("--alpha", dict(type=float, default=1.0)), ("--m", dict(type=float, default=3.0))],
+                  nugget=1e-13, N_domain=900, N_boundary=124, GNsteps=4).parse_args()
 if cfg.randomseed is not None:
     onp.random.seed(cfg.randomseed)
 solver = solver_GP(cfg, PDE_type="Nonlinear_elliptic")
@@ -55,10 +34,7 @@ if cfg.show_figure:
 solver.solve(method=cfg.method, pen_lambda=cfg.pen_lambda, print_option=cfg.print_hist)
 pts_truth = u(solver.eqn.X_domain[:, 0], solver.eqn.X_domain[:, 1])
 solver.collocation_pts_err(pts_truth)
-N_pts = 60
-xx = onp.linspace(0, 1, N_pts)
-XX, YY = onp.meshgrid(xx, xx)
-X_test = onp.concatenate((XX.reshape(-1, 1), YY.reshape(-1, 1)), axis=1)
+XX, YY, X_test = unit_grid(60)
 solver.test(X_test)
 solver.get_test_error(u(X_test[:, 0], X_test[:, 1]))
 if cfg.show_figure:
