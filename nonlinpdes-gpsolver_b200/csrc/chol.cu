@@ -17,7 +17,8 @@ constexpr int BASE = 64;
 constexpr int LDS_PAD = BASE + 1;
 
 // ---------------------------------------------------------------------------
-// potrf of one diagonal block (n <= 64) held in shared memory, right-looking.
+// potrf of one diagonal block (n <= 64) held in shared memory: one thread per row, left-looking,
+// each entry reduced progressively in column order (same rounding model as the GEMM updates).
 // A non-positive / NaN pivot is recorded once in *info (1-based global index);
 // sqrt then produces NaN which propagates, like jnp.linalg.cholesky's NaN output.
 // ---------------------------------------------------------------------------
