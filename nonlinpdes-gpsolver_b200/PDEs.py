@@ -210,6 +210,15 @@ class _GPProblem(object):
         self.sol_sampled_pts = sol[:self.N_domain]
         self._state = 'solved'
 
+    # ---- optional checkpoint of a finished solve (the reference only has commented-out np.savez calls)
+    _STATE_KEYS = ('X_domain', 'X_boundary', 'rhs_f', 'bdy_g', 'sol', 'sol_vec', 'sol_sampled_pts', 'loss_hist', 'init_sol')
+
+    def save_solution(self, path):
+        """np.savez of the points, data vectors, iterate, loss history and kernel / nugget settings."""
+        onp.savez(path, kernel=str(self.kernel), kernel_parameter=onp.asarray(self.kernel_parameter, dtype=onp.float64),
+                  nugget=float(self.nugget), nugget_type=str(self.nugget_type),
+                  **{k: onp.asarray(getattr(self, k)) for k in self._STATE_KEYS if hasattr(self, k)})
+
     def extend_sol(self, X_test):
         """src/PDEs.py:203-208: Theta_test @ (L^T \\ (L \\ sol_vec)); Theta_test is never formed."""
         eng = self._engine()

@@ -4,7 +4,15 @@
 
 #include <cstring>
 
+#include <nvtx3/nvToolsExt.h>   // header-only; ranges are no-ops unless a profiler (ncu / nsys) is attached
+
 namespace {
+
+// NVTX range per hot-path phase (the reference has no tracing at all)
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 __global__ void get_diag_kernel(const double* __restrict__ T, long ld, int M, double* __restrict__ out) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -190,6 +198,7 @@ int gpp_set_points(gpp_handle* h, const double* Xd, int N, const double* Xb, int
 }
 
 int gpp_gram_assemble(gpp_handle* h, int slot, int layout, int kernel, const double* kparams) {
+  NvtxRange nvtx_range("gpp:gram_assemble");
   if (h) cudaSetDevice(h->device);
   if (bad_slot(h, slot, false)) return -2;
   if (!h->Xall) { h->err = "points not set"; return -1; }
@@ -300,6 +309,7 @@ int gpp_gram_upload(gpp_handle* h, int slot, const double* theta) {
 }
 
 int gpp_potrf(gpp_handle* h, int slot, int* info) {
+  NvtxRange nvtx_range("gpp:potrf");
   if (h) cudaSetDevice(h->device);
   if (bad_slot(h, slot)) return -2;
   CUDA_TRY(h, cudaSetDevice(h->device));
@@ -317,6 +327,7 @@ int gpp_potrf(gpp_handle* h, int slot, int* info) {
 }
 
 int gpp_inverse(gpp_handle* h, int slot) {
+  NvtxRange nvtx_range("gpp:inverse");
   if (h) cudaSetDevice(h->device);
   if (bad_slot(h, slot)) return -2;
   CUDA_TRY(h, cudaSetDevice(h->device));
@@ -454,6 +465,7 @@ static int gn_check(gpp_handle* h, bool need_inverse) {
 }
 
 int gpp_gn_loss(gpp_handle* h, double* loss) {
+  NvtxRange nvtx_range("gpp:gn_loss");
   if (h) cudaSetDevice(h->device);
   int rc = gn_check(h, false);
   if (rc) return rc;
@@ -463,6 +475,7 @@ int gpp_gn_loss(gpp_handle* h, double* loss) {
 }
 
 int gpp_gn_step(gpp_handle* h, double step, double* loss) {
+  NvtxRange nvtx_range("gpp:gn_step");
   if (h) cudaSetDevice(h->device);
   int rc = gn_check(h, true);
   if (rc) return rc;
@@ -522,6 +535,7 @@ int gpp_gn_coef(gpp_handle* h, int slot, int p, int q, double* c_out, int* prese
 }
 
 int gpp_predict(gpp_handle* h, int slot, const double* Xtest, int ntest, const double* w, double* out) {
+  NvtxRange nvtx_range("gpp:predict");
   if (h) cudaSetDevice(h->device);
   if (bad_slot(h, slot)) return -2;
   if (!Xtest || ntest <= 0 || !w || !out) return -3;

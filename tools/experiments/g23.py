@@ -1,4 +1,4 @@
-import sys, time; sys.path.insert(0,'/root/repo')
+import sys, time; sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__)))))
 import numpy as np
 from oracle import gp_oracle as o
 from scipy.interpolate import griddata
