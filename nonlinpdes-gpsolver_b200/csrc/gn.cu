@@ -404,8 +404,6 @@ int gn_grad_hess(gpp_handle* h) {
 // One GN step at g.z; requires F, s and coef of g.z to be current (gn_loss leaves them so).
 int gn_step(gpp_handle* h, double step, double* loss_host) {
   GnState& g = h->gn;
-  const int ns = nslots_of(g);
-  const int N = h->N;
   set_kind(g);
   int rc;
   static const bool trace = getenv("GPP_TRACE") != nullptr;
