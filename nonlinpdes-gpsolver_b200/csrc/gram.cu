@@ -98,12 +98,13 @@ constexpr int TP = 64;            // points per tile side
 constexpr int SPAD = TP + 1;      // stash row stride (doubles)
 constexpr int ASM_SMEM = (3 * TP * SPAD + 4 * TP) * 8;
 
+// Theta is written once and is far larger than L2: streaming (evict-first) stores
 __device__ __forceinline__ void store_pair(double* dst, double e0, double e1, bool ok0, bool ok1, bool vec) {
   if (ok0 && ok1 && vec) {
-    *reinterpret_cast<double2*>(dst) = make_double2(e0, e1);
+    __stcs(reinterpret_cast<double2*>(dst), make_double2(e0, e1));
   } else {
-    if (ok0) dst[0] = e0;
-    if (ok1) dst[1] = e1;
+    if (ok0) __stcs(dst, e0);
+    if (ok1) __stcs(dst + 1, e1);
   }
 }
 
