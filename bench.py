@@ -175,7 +175,7 @@ def main():
     ap.add_argument("--N_domain", type=int, default=40000)
     ap.add_argument("--gn_steps", type=int, default=4)
     ap.add_argument("--nugget", type=float, default=1e-12)   # 1e-13 is numerically indefinite at N>=20k
-    ap.add_argument("--cpu_sample_N", type=int, default=2000)
+    ap.add_argument("--cpu_sample_N", type=int, default=4000)    # ~15-20 s of CPU work on a 16-core host
     ap.add_argument("--skip_cpu_baseline", action="store_true")
     a = ap.parse_args()
 
