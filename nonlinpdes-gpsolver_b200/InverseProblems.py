@@ -48,15 +48,22 @@ class Darcy_flow2d(_GPProblem):
         if add_u is not None:
             eng.gram_add_diag(0, add_u)
             eng.gram_add_diag(1, add_a)
+        self._nugget_add = (add_u, add_a)
         self._state = 'gram'
 
     @property
     def Theta_u(self):
+        if self._state in ('chol', 'solved'):       # overwritten by L_u on the device: re-assemble on request
+            return self._reassemble('Darcy_flow2d', self._nugget_add[0])
         return self._dense(0, 0, ('gram',))
 
     @property
     def Theta_a(self):
+        if self._state in ('chol', 'solved'):
+            return self._reassemble('Darcy_flow2d_a', self._nugget_add[1])
         return self._dense(1, 0, ('gram',))
+
+    Theta = Theta_u
 
     @property
     def L_u(self):
@@ -72,6 +79,8 @@ class Darcy_flow2d(_GPProblem):
         return self._engine().gram_download(slot, what)
 
     def Gram_Cholesky(self):
+        if self._state in ('chol', 'solved'):
+            return
         eng = self._engine()
         eng.timer_start()
         self.chol_info = (eng.potrf(0), eng.potrf(1))
@@ -87,6 +96,18 @@ class Darcy_flow2d(_GPProblem):
             self._engine().inverse(0)
             self._engine().inverse(1)
             self._inverted = True
+
+    def GN_loss(self, z, z_old):
+        """src/InverseProblems.py:127-147."""
+        N = self.N_domain
+        z, zo = onp.asarray(z, dtype=onp.float64), onp.asarray(z_old, dtype=onp.float64)
+        w0_old, w1_old, w2_old, v1_old, v2_old = zo[:N], zo[N:2 * N], zo[2 * N:3 * N], zo[4 * N:5 * N], zo[5 * N:6 * N]
+        w0, w1, w2, v0, v1, v2 = (z[k * N:(k + 1) * N] for k in range(6))
+        v3 = (-self.rhs_f) * (-onp.exp(-w0_old)) * w0 + (-v1_old) * w1 + (-v2_old) * w2 + (-w1_old) * v1 + (-w2_old) * v2
+        w_all = onp.concatenate((w1, w2, w0), axis=0)
+        v_all = onp.concatenate((v1, v2, v3, v0, self.bdy_g), axis=0)
+        return (self._quad(1, w_all) + self._quad(0, v_all)
+                + (1 / self.noise_level ** 2) * float(onp.sum((v0[:self.N_data] - self.data_u) ** 2)))
 
     def GN_method(self, max_iter=3, step_size=1, initial_sol='rdm', print_hist=True):
         """src/InverseProblems.py:153-186."""

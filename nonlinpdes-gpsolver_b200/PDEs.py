@@ -17,12 +17,16 @@ def eval_on_points(fun, X):
         return onp.zeros(0)
     try:
         v = onp.asarray(fun(x1, x2), dtype=onp.float64)
-        if v.shape == (n,):
-            return v
-        if v.shape == ():
+    except (TypeError, ValueError):
+        v = None
+    if v is not None and v.shape == (n,):
+        return v
+    if v is not None and v.shape == ():
+        # a 0-d result is either a constant function (bdy = lambda x1, x2: 0) or a callable that reduces over its
+        # inputs; only the former may be broadcast, so check it against per-point scalar calls at both ends
+        ends = [float(fun(float(x1[k]), float(x2[k]))) for k in (0, n - 1)]
+        if ends[0] == float(v) and ends[1] == float(v):
             return onp.full(n, float(v))
-    except Exception:
-        pass
     return onp.array([float(fun(float(a), float(b))) for a, b in zip(x1, x2)], dtype=onp.float64)
 
 
@@ -103,14 +107,27 @@ class _GPProblem(object):
             self.ratio = ratio[0] if len(ratio) == 1 else ratio
         if add is not None:
             eng.gram_add_diag(0, add)
+        self._nugget_add = add
         self._state = 'gram'
 
     # Theta / L are lazy: dense download only when somebody asks (tests, small problems)
     @property
     def Theta(self):
-        if self._state not in ('gram',):
-            raise RuntimeError("Theta was overwritten in place by its Cholesky factor; read it before Gram_Cholesky()")
-        return self._engine().gram_download(0, 0)
+        """The reference keeps ``self.Theta`` (src/PDEs.py:69); here the device copy is overwritten in place by its
+        Cholesky factor, so after Gram_Cholesky() a read re-assembles it (same kernel, same nugget) on a scratch handle."""
+        if self._state == 'gram':
+            return self._engine().gram_download(0, 0)
+        if self._state in ('chol', 'solved'):
+            return self._reassemble(self._eqn, self._nugget_add)
+        raise RuntimeError("call Gram_matrix() first")
+
+    def _reassemble(self, layout, add):
+        eng = _lib.default_engine()
+        eng.set_points(self.X_domain, self.X_boundary)
+        eng.gram_assemble(0, layout, self.kernel, self.kernel_parameter)
+        if add is not None:
+            eng.gram_add_diag(0, add)
+        return eng.gram_download(0, 0)
 
     @property
     def L(self):
@@ -121,12 +138,19 @@ class _GPProblem(object):
     def Gram_Cholesky(self):
         """jnp.linalg.cholesky(self.Theta) (src/PDEs.py:75-80).  Like JAX, failure does not raise: the
         factor carries NaNs and the loss turns NaN; the pivot index is kept in ``self.chol_info``."""
+        if self._state in ('chol', 'solved'):
+            return                                  # already factored (the reference would recompute the same L)
         eng = self._engine()
         eng.timer_start()
         self.chol_info = eng.potrf(0)
         self.timings['potrf_ms'] = eng.timer_stop()
         self._inverted = False
         self._state = 'chol'
+
+    def _quad(self, slot, r):
+        """r^T Theta^{-1} r = |L^{-1} r|^2 of the reference's linearised losses, by two triangular solves."""
+        r = onp.ascontiguousarray(r, dtype=onp.float64)
+        return float(onp.dot(r, self._engine().solve_vec(slot, r)))
 
     # ---- loss / GN ----
     def _gn_params(self):
@@ -244,11 +268,38 @@ class Nonlinear_elliptic2d(_GPProblem):
     def Gram_matrix(self, kernel='Gaussian', kernel_parameter=0.2, nugget=1e-8, nugget_type='adaptive'):
         self._gram(kernel, kernel_parameter, nugget, nugget_type)
 
-    def loss_relaxed(self, z, pen_lambda):
+    def GN_loss(self, z, z_old):
+        """src/PDEs.py:94-98 (the linearised loss whose Hessian is Hessian_GN)."""
+        z, z_old = onp.asarray(z, dtype=onp.float64), onp.asarray(z_old, dtype=onp.float64)
+        zz = onp.append(self.alpha * self.m * (z_old ** (self.m - 1)) * (z - z_old), z)
+        return self._quad(0, onp.append(zz, self.bdy_g))
+
+    def _relaxed_at(self, z, pen_lambda):
         eng = self._engine()
         eng.gn_setup('Nonlinear_elliptic_relaxed', [float(self.alpha), float(self.m), float(pen_lambda)], self.rhs_f, self.bdy_g)
         eng.gn_set_z(z)
-        return eng.gn_loss()
+        return eng
+
+    def loss_relaxed(self, z, pen_lambda):
+        return self._relaxed_at(z, pen_lambda).gn_loss()
+
+    def grad_loss_relaxed(self, z, pen_lambda):
+        """src/PDEs.py:150-152."""
+        self._ensure_inverse()
+        return self._relaxed_at(z, pen_lambda).gn_grad_hess(True, False)[0]
+
+    def GN_loss_relaxed(self, z, z_old, pen_lambda):
+        """src/PDEs.py:155-165."""
+        N = self.N_domain
+        z, z_old = onp.asarray(z, dtype=onp.float64), onp.asarray(z_old, dtype=onp.float64)
+        v, w, w_old = z[:N], z[N:], z_old[N:]
+        ss2 = -v + self.alpha * self.m * (w_old ** (self.m - 1)) * (w - w_old) - self.rhs_f
+        return self._quad(0, onp.append(onp.append(v, w), self.bdy_g)) + float(onp.dot(ss2, ss2)) / pen_lambda
+
+    def Hessian_GN_relaxed(self, z, z_old, pen_lambda):
+        """src/PDEs.py:168-169; depends on z_old only."""
+        self._ensure_inverse()
+        return self._relaxed_at(z_old, pen_lambda).gn_grad_hess(False, True)[1]
 
     def GN_relaxed_method(self, max_iter=3, step_size=1, initial_sol='rdm', pen_lambda=1e-10, print_hist=True):
         """src/PDEs.py:171-201: unknowns z = [v; w] (2N), penalised constraint -v + alpha w^m = f.
@@ -288,6 +339,8 @@ class Nonlinear_elliptic2d(_GPProblem):
         self.sol = sol
         self.sol_vec = onp.append(sol, self.bdy_g)        # :199
         self.sol_sampled_pts = sol[N:]                    # :201
+        self._inverted = True
+        self._state = 'solved'
 
 
 class Burgers(_GPProblem):
@@ -319,6 +372,15 @@ class Eikonal(_GPProblem):
 
     def _gn_params(self):
         return [float(self.eps)]
+
+    def GN_loss(self, z, z_old):
+        """src/PDEs.py:437-451."""
+        N = self.N_domain
+        z, z_old = onp.asarray(z, dtype=onp.float64), onp.asarray(z_old, dtype=onp.float64)
+        v1_old, v2_old = z_old[N:2 * N], z_old[2 * N:]
+        v0, v1, v2 = z[:N], z[N:2 * N], z[2 * N:]
+        v3 = -(self.rhs_f ** 2 - 2 * v1 * v1_old - 2 * v2 * v2_old) / self.eps
+        return self._quad(0, onp.concatenate((v1, v2, v3, v0, self.bdy_g)))
 
     def Gram_matrix(self, kernel='Gaussian', kernel_parameter=0.2, nugget=1e-8, nugget_type='adaptive'):
         self._gram(kernel, kernel_parameter, nugget, nugget_type)

@@ -39,11 +39,8 @@ __global__ void unpack_kernel(const double* __restrict__ in, int M, double* __re
   if (j <= i) T[(long)i * ld + j] = in[e];
 }
 
-int dev_alloc(gpp_handle* h, double** p, size_t n) {
-  if (*p) { cudaFree(*p); *p = nullptr; }
-  CUDA_TRY(h, cudaMalloc(p, n * sizeof(double)));
-  return GPP_OK;
-}
+// grow-only device buffers (gpp_internal.cuh: dev_reserve): repeated solves on a handle never touch the allocator
+int dev_alloc(gpp_handle* h, double** p, size_t n) { return dev_reserve(h, p, n); }
 void dev_free(double*& p) { if (p) { cudaFree(p); p = nullptr; } }
 
 int ensure_work(gpp_handle* h, size_t bytes) {
@@ -102,6 +99,7 @@ int gpp_destroy(gpp_handle* h) {
   if (!h) return -1;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
+  if (h->dist) gpp_dist_finalize(h);       // NCCL communicator + the distributed buffers
   dev_free(h->Xd); dev_free(h->Xb); dev_free(h->Xall);
   for (auto& s : h->slot) { dev_free(s.T); dev_free(s.udiag); dev_free(s.Ainv); }
   GnState& g = h->gn;
@@ -213,14 +211,11 @@ int gpp_gram_assemble(gpp_handle* h, int slot, int layout, int kernel, const dou
   int o = 0;
   for (int p = 0; p < s.lay.nblk; ++p) { s.off[p] = o; o += s.N + (s.lay.with_bdy[p] ? s.Nb : 0); }
   s.off[s.lay.nblk] = o;
-  const int Mnew = o;
-  const long ldnew = round_up(Mnew, 16);
-  if (!s.T || Mnew != s.M || ldnew != s.ld) {
-    s.M = Mnew; s.ld = ldnew;
+  s.M = o; s.ld = round_up(s.M, 16);
+  {
     int rc = dev_alloc(h, &s.T, (size_t)s.M * s.ld);
     if (rc) return rc;
-    dev_free(s.udiag); dev_free(s.Ainv);
-    rc = make_tensor_map(h, &s.mapT, s.T, s.M, s.M, s.ld);
+    rc = make_tensor_map(h, &s.mapT, s.T, s.M, s.M, s.ld);     // host-side encode only; M / ld may have changed
     if (rc) return rc;
   }
   s.Mint = s.lay.nblk * s.N;
@@ -340,10 +335,8 @@ int gpp_inverse(gpp_handle* h, int slot) {
   rc = make_tensor_map(h, &s.mapUdiag, s.udiag, s.M, NB, NB);
   if (rc) return rc;
   s.ldA = round_up(s.Mint, 16);
-  if (!s.Ainv) {
-    rc = dev_alloc(h, &s.Ainv, (size_t)s.Mint * s.ldA);
-    if (rc) return rc;
-  }
+  rc = dev_alloc(h, &s.Ainv, (size_t)s.Mint * s.ldA);          // sized for the present Mint (grow-only)
+  if (rc) return rc;
   rc = inverse_interior(h, s);
   if (rc) return rc;
   s.inverted = true;

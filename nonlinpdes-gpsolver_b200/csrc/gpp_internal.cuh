@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -115,6 +116,9 @@ struct gpp_handle {
   long launches = 0;
   // distributed (dist.cu)
   void* dist = nullptr;
+  // capacity (doubles) of every device buffer obtained through dev_reserve, keyed by the address of its pointer:
+  // buffers are grown, never shrunk, so repeated solves on one handle do not touch the allocator
+  std::map<double**, size_t> caps;
 };
 
 #define GPP_OK 0
@@ -130,6 +134,22 @@ struct gpp_handle {
   } while (0)
 
 static inline long round_up(long x, long m) { return (x + m - 1) / m * m; }
+
+// *p holds at least n doubles afterwards; reallocates (contents lost) only when the present buffer is too small
+static inline int dev_reserve(gpp_handle* h, double** p, size_t n) {
+  if (n == 0) n = 1;
+  auto it = h->caps.find(p);
+  if (*p && it != h->caps.end() && it->second >= n) return GPP_OK;
+  if (*p) { cudaFree(*p); *p = nullptr; }
+  h->caps.erase(p);
+  CUDA_TRY(h, cudaMalloc(p, n * sizeof(double)));
+  h->caps[p] = n;
+  return GPP_OK;
+}
+static inline void dev_release(gpp_handle* h, double** p) {
+  if (*p) { cudaFree(*p); *p = nullptr; }
+  h->caps.erase(p);
+}
 
 // ---- gemm_dmma.cu -----------------------------------------------------------
 struct GemmDesc {

@@ -238,14 +238,22 @@ class _Solver:
     def __init__(self, L, solve="lu"):
         self.L = L
         self.mode = solve
-        if solve == "lu" and np.all(np.isfinite(L)):
-            self.lu = sla.lu_factor(L)
-        elif solve == "lu":
+        self.n_factorizations = 0
+        if solve in ("lu", "lu_percall") and not np.all(np.isfinite(L)):
             self.mode = "nan"
+        elif solve == "lu":
+            self.lu = sla.lu_factor(L)
+            self.n_factorizations = 1
 
     def fwd(self, b):
         if self.mode == "nan":
             return np.full_like(np.asarray(b, dtype=float), np.nan)
+        if self.mode == "lu_percall":
+            # cost model of the reference: every jnp.linalg.solve(self.L, .) call inside loss / GN_loss
+            # (src/PDEs.py:86,97) refactorises L by getrf; the backward solve of the same call reuses that LU
+            self.lu = sla.lu_factor(self.L)
+            self.n_factorizations += 1
+            return sla.lu_solve(self.lu, b)
         if self.mode == "lu":
             return sla.lu_solve(self.lu, b)
         return sla.solve_triangular(self.L, b, lower=True)
@@ -253,7 +261,7 @@ class _Solver:
     def bwd(self, b):  # L^{-T} b
         if self.mode == "nan":
             return np.full_like(np.asarray(b, dtype=float), np.nan)
-        if self.mode == "lu":
+        if self.mode in ("lu", "lu_percall"):
             return sla.lu_solve(self.lu, b, trans=1)
         return sla.solve_triangular(self.L, b, lower=True, trans="T")
 
@@ -300,9 +308,19 @@ class _Problem:
         if self.ratio is not None and len(self.ratio) == 1:
             self.ratio = self.ratio[0]
 
-    def Gram_Cholesky(self, solve="lu"):
+    def Gram_Cholesky(self, solve="lu", structured=False):
+        """structured=True: Hessian_GN is formed from the interior block of Theta^{-1} (LAPACK dpotri) and the
+        diagonal coefficient form of J instead of the dense M x n solves -- the same matrix, affordable at
+        N_domain ~ 10^4 (tests/test_gpu_configs.py); checked against the dense form in tests/test_oracle_golden.py."""
         self.L = cholesky_lower(self.Theta)
         self._s = _Solver(self.L, solve)
+        self._Ainv = None
+        if structured:
+            inv, info = sla.lapack.dpotri(self.L, lower=1)
+            assert info == 0
+            mint = len(LAYOUT[self.eqn]) * self.N_domain
+            inv = inv[:mint, :mint]
+            self._Ainv = np.tril(inv) + np.tril(inv, -1).T
 
     # -- dense Jacobian from the coefficient form
     def jacobian(self, z):
@@ -324,8 +342,21 @@ class _Problem:
 
     def Hessian_GN(self, z):
         # hessian(GN_loss)(z, z) = J^T L^{-T} 2 L^{-1} J   (src/PDEs.py:101-102)
+        if getattr(self, "_Ainv", None) is not None:
+            return self._hessian_structured(z)
         J = self.jacobian(z)
         return J.T @ self._s.bwd(2.0 * self._s.fwd(J))
+
+    def _hessian_structured(self, z):
+        N, nz = self.N_domain, self.n_blocks
+        cf = self.jac_coeffs(z)
+        H = np.zeros((nz * N, nz * N))
+        for (p, q), c in cf.items():
+            c = np.broadcast_to(np.asarray(c, dtype=float), (N,))
+            for (pp, qq), cc in cf.items():
+                cc = np.broadcast_to(np.asarray(cc, dtype=float), (N,))
+                H[q * N:(q + 1) * N, qq * N:(qq + 1) * N] += 2.0 * (c[:, None] * self._Ainv[p * N:(p + 1) * N, pp * N:(pp + 1) * N]) * cc[None, :]
+        return H
 
     def init_guess(self, initial_sol):
         n = self.n_blocks * self.N_domain

@@ -83,3 +83,28 @@ def test_darcy_notebook():
     d.Gram_Cholesky("lu")
     d.GN_method(g["steps"], 1, init)
     np.testing.assert_allclose(d.loss_hist, g["loss_hist"], rtol=2e-9)
+
+
+def test_structured_hessian_and_percall_lu_equal_dense_oracle():
+    """The two cost-model variants of the oracle (Hessian from the interior inverse block; LU of L redone per call like
+    the reference's jnp.linalg.solve) give the same numbers as the default dense / factor-once form."""
+    np.random.seed(7)
+    N, Nb = 80, 24
+    Xd, Xb = o.sampled_pts_rdm(N, Nb, np.array([[0.0, 1.0], [0.0, 1.0]]))
+    for make, nz, init in ((lambda: o.Nonlinear_elliptic2d(1.0, 3), 1, None), (lambda: o.Eikonal(0.1), 3, "zero")):
+        runs = []
+        z0 = np.random.normal(0.0, 1.0, nz * N) if init is None else init
+        for solve, structured in (("lu", False), ("tri", True), ("lu_percall", False)):
+            p = make()
+            p.set_points(Xd, Xb, o.elliptic_f(Xd[:, 0], Xd[:, 1]) if nz == 1 else np.ones(N),
+                         o.elliptic_u(Xb[:, 0], Xb[:, 1]) if nz == 1 else np.zeros(Xb.shape[0]))
+            p.Gram_matrix("Gaussian", 0.2, 1e-6, "adaptive")
+            p.Gram_Cholesky(solve, structured=structured)
+            p.GN_method(3, 1, z0)
+            runs.append(p)
+        z = runs[0].sol
+        H0, H1 = runs[0].Hessian_GN(z), runs[1].Hessian_GN(z)
+        assert np.max(np.abs(H0 - H1)) <= 1e-7 * np.max(np.abs(H0))
+        np.testing.assert_allclose(runs[1].loss_hist, runs[0].loss_hist, rtol=1e-8)
+        np.testing.assert_allclose(runs[2].loss_hist, runs[0].loss_hist, rtol=1e-12)
+        assert runs[2]._s.n_factorizations >= 3 * 3 and runs[0]._s.n_factorizations == 1
