@@ -105,22 +105,33 @@ int gpp_theta_test(gpp_handle* h, int slot, const double* X_test, int N_test, do
 int gpp_kernel_eval(gpp_handle* h, int kernel, const double* kparams, int op_x, int op_y, const double* x1,
                     const double* x2, const double* y1, const double* y2, long n, double* out);
 
-/* ---- multi-GPU: one process per GPU, block rows of Theta dealt cyclically (P x 1 block-cyclic), NCCL over NVLink.
- * New functionality (the reference is single-process).  Rank 0 creates the 128-byte NCCL id and
- * distributes it out of band (torch.distributed / MPI / a file); every rank then calls gpp_dist_init. */
+/* ---- multi-GPU: ONE problem sharded over the GPUs of a box (new functionality: the reference is single-process,
+ * SURVEY section 2).  One process per GPU; NCCL over NVLink.  Storage is replicated, work is owner-computes on a
+ * P x Q block-cyclic grid of NB x NB blocks (default P = world, Q = 1); finished panels are gathered with NCCL.
+ * Rank 0 creates the 128-byte NCCL id and distributes it out of band (torch.distributed / MPI / a file); every rank
+ * then calls gpp_dist_init.  All ranks must set the same points and make the same calls in the same order. */
 int gpp_dist_unique_id(unsigned char* id128);
 int gpp_dist_init(gpp_handle* h, int rank, int world, const unsigned char* id128);
+/* tests: run the plans of `nranks` ranks one after the other on this one GPU (no NCCL, shared storage) */
+int gpp_dist_init_virtual(gpp_handle* h, int nranks);
+/* process grid, P * Q = number of ranks; block (bi, bc) belongs to rank (bi mod P) * Q + (bc mod Q) */
+int gpp_dist_set_grid(gpp_handle* h, int P, int Q);
+int gpp_dist_info(gpp_handle* h, int* rank, int* world, int* P, int* Q);
 int gpp_dist_finalize(gpp_handle* h);
-/* row-sharded Gram_matrix_assembly: this rank's block rows (NB rows each, block b on rank b % world), no exchange */
+/* sharded Gram_matrix_assembly into slot 0: this rank's block rows (bi mod P == p), no exchange */
 int gpp_dist_gram_assemble(gpp_handle* h, int layout, int kernel, const double* kparams);
-int gpp_dist_local_rows(gpp_handle* h, int* n_local_rows, int* M);
-/* nugget support: full diagonal on every rank (all-reduce) / add a full-length vector to the owned diagonal entries */
+/* nugget support: full diagonal on every rank (all-reduce) / add a full-length vector to the held diagonal entries */
 int gpp_dist_get_diag(gpp_handle* h, double* diag_out);
 int gpp_dist_add_diag(gpp_handle* h, const double* add);
-/* distributed Gram_Cholesky: per block column one ncclBroadcast of the factored block row, then local DMMA updates */
+/* distributed X.Gram_Cholesky of slot 0 (right-looking, look-ahead, one panel gather per block column).  Afterwards every
+ * rank holds the whole factor: gpp_gn_loss, gpp_solve_vec, gpp_predict, gpp_gram_download(h, 0, 1, .) work on any rank. */
 int gpp_dist_potrf(gpp_handle* h, int* info);
-/* this rank's rows (n_local_rows x M, dense, zeros above the diagonal): tests / gathering L */
-int gpp_dist_download_local(gpp_handle* h, double* out);
+/* distributed counterpart of gpp_inverse (elliptic layout): U = L^{-T} sharded then replicated, and the sub-blocks of the
+ * interior block of Theta^{-1} that this rank's Hessian blocks need */
+int gpp_dist_inverse(gpp_handle* h);
+/* gpp_gn_step with the Hessian assembled block-wise by the owners and factorised by the distributed Cholesky; z and the
+ * returned loss are identical on every rank (PDE id GPP_PDE_ELLIPTIC only) */
+int gpp_dist_gn_step(gpp_handle* h, double step_size, double* loss);
 
 #ifdef __cplusplus
 }

@@ -4,7 +4,7 @@ Cholesky factor, the interior block of Theta^{-1} and the GN iterate live on the
 import numpy as onp
 from numpy import random
 
-from . import _lib
+from . import _dist, _lib
 from .sample_points import sampled_pts_rdm, sampled_pts_grid
 
 
@@ -41,6 +41,7 @@ class _GPProblem(object):
         self.rhs = rhs
         self.domain = domain
         self._eng = None
+        self._sharded = False
         self.timings = {}
 
     # reference helpers
@@ -54,6 +55,25 @@ class _GPProblem(object):
         if self._eng is None:
             self._eng = _lib.Engine()
         return self._eng
+
+    # ---- multi-GPU: ONE solve sharded over the GPUs of the box (no counterpart in the reference) ----
+    def shard(self, dist=None, virtual_ranks=None, Q=None):
+        """Shard this problem over the ranks of an initialised ``torch.distributed`` group (one process per GPU; every
+        rank must construct the same problem with the same points and make the same calls).  Gram assembly, Cholesky,
+        the inverse and the GN Hessian are then owner-computes over a P x Q block-cyclic grid with NCCL panel gathers
+        (csrc/dist.cu); all results (loss history, solution, predictions) are identical on every rank.
+        ``virtual_ranks=n`` instead emulates n ranks on this one GPU (tests)."""
+        if self._eqn != 'Nonlinear_elliptic':
+            raise NotImplementedError("the sharded path covers Nonlinear_elliptic2d (BASELINE configs[4]); "
+                                      "the small configurations are latency-bound and run as replicas")
+        eng = self._engine()
+        if virtual_ranks is not None:
+            eng.dist_init_virtual(virtual_ranks)
+            eng.dist_set_grid(*_dist.grid_shape(virtual_ranks, Q))
+        else:
+            _dist.init_engine_distributed(eng, dist, Q)
+        self._sharded = True
+        return self
 
     # ---- sampling (src/PDEs.py:34-54) ----
     def sampled_pts(self, N_domain, N_boundary, sampled_type='random'):
@@ -99,14 +119,21 @@ class _GPProblem(object):
         self.nugget_type, self.nugget = nugget_type, nugget
         self.kernel, self.kernel_parameter = kernel, kernel_parameter
         eng.timer_start()
-        eng.gram_assemble(0, self._eqn, kernel, kernel_parameter)
+        if self._sharded:
+            eng.dist_gram_assemble(self._eqn, kernel, kernel_parameter)
+        else:
+            eng.gram_assemble(0, self._eqn, kernel, kernel_parameter)
         self.timings['assembly_ms'] = eng.timer_stop()
         n_blocks = {'Nonlinear_elliptic': 2}.get(self._eqn, 4)
-        add, ratio = self._nugget_vector(eng.gram_get_diag(0), n_blocks, nugget, nugget_type)
+        diag = eng.dist_get_diag() if self._sharded else eng.gram_get_diag(0)
+        add, ratio = self._nugget_vector(diag, n_blocks, nugget, nugget_type)
         if ratio is not None:
             self.ratio = ratio[0] if len(ratio) == 1 else ratio
         if add is not None:
-            eng.gram_add_diag(0, add)
+            if self._sharded:
+                eng.dist_add_diag(add)
+            else:
+                eng.gram_add_diag(0, add)
         self._nugget_add = add
         self._state = 'gram'
 
@@ -115,9 +142,9 @@ class _GPProblem(object):
     def Theta(self):
         """The reference keeps ``self.Theta`` (src/PDEs.py:69); here the device copy is overwritten in place by its
         Cholesky factor, so after Gram_Cholesky() a read re-assembles it (same kernel, same nugget) on a scratch handle."""
-        if self._state == 'gram':
+        if self._state == 'gram' and not self._sharded:
             return self._engine().gram_download(0, 0)
-        if self._state in ('chol', 'solved'):
+        if self._state in ('gram', 'chol', 'solved'):
             return self._reassemble(self._eqn, self._nugget_add)
         raise RuntimeError("call Gram_matrix() first")
 
@@ -142,7 +169,7 @@ class _GPProblem(object):
             return                                  # already factored (the reference would recompute the same L)
         eng = self._engine()
         eng.timer_start()
-        self.chol_info = eng.potrf(0)
+        self.chol_info = eng.dist_potrf() if self._sharded else eng.potrf(0)
         self.timings['potrf_ms'] = eng.timer_stop()
         self._inverted = False
         self._state = 'chol'
@@ -174,6 +201,8 @@ class _GPProblem(object):
         return eng
 
     def _ensure_inverse(self):
+        if self._sharded:
+            raise NotImplementedError("dense grad_loss / Hessian_GN read-outs are not available on a sharded problem")
         if not getattr(self, '_inverted', False):
             self._engine().inverse(0)
             self._inverted = True
@@ -205,9 +234,12 @@ class _GPProblem(object):
         self.init_sol = sol
         self._setup_gn()
         eng.timer_start()
-        eng.inverse(0)
+        if self._sharded:
+            eng.dist_inverse()
+        else:
+            eng.inverse(0)
+            self._inverted = True
         self.timings['inverse_ms'] = eng.timer_stop()
-        self._inverted = True
         eng.gn_set_z(sol)
         loss_hist = []
         eng.timer_start()
@@ -217,8 +249,9 @@ class _GPProblem(object):
             print('[Error] Loss is nan: maybe nugget is too small!')
         if print_hist:
             print('iter = 0', 'Loss =', loss_now)
+        gn_step = eng.dist_gn_step if self._sharded else eng.gn_step
         for iter_step in range(1, max_iter + 1):
-            loss_now = eng.gn_step(step_size)
+            loss_now = gn_step(step_size)
             if onp.isnan(loss_now):
                 print('[Error] Loss is nan: maybe nugget is too small!')
             loss_hist.append(loss_now)

@@ -58,13 +58,16 @@ def _sig(lib):
         "gpp_kernel_eval": [H, C.c_int, _dp, C.c_int, C.c_int, _dp, _dp, _dp, _dp, C.c_long, _dp],
         "gpp_dist_unique_id": [C.POINTER(C.c_ubyte)],
         "gpp_dist_init": [H, C.c_int, C.c_int, C.POINTER(C.c_ubyte)],
+        "gpp_dist_init_virtual": [H, C.c_int],
+        "gpp_dist_set_grid": [H, C.c_int, C.c_int],
+        "gpp_dist_info": [H, _ip, _ip, _ip, _ip],
         "gpp_dist_finalize": [H],
         "gpp_dist_gram_assemble": [H, C.c_int, C.c_int, _dp],
-        "gpp_dist_local_rows": [H, _ip, _ip],
         "gpp_dist_get_diag": [H, _dp],
         "gpp_dist_add_diag": [H, _dp],
         "gpp_dist_potrf": [H, _ip],
-        "gpp_dist_download_local": [H, _dp],
+        "gpp_dist_inverse": [H],
+        "gpp_dist_gn_step": [H, C.c_double, _dp],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)
@@ -312,11 +315,24 @@ class Engine:
         return out.reshape(shape)
 
 
-    # ---- multi-GPU (one process per GPU); see _dist.py for the torch.distributed plumbing
+    # ---- multi-GPU: one problem sharded over the GPUs of a box (one process per GPU); see _dist.py for the plumbing
     def dist_init(self, rank, world, id_bytes):
         buf = (C.c_ubyte * 128).from_buffer_copy(bytes(id_bytes))
         self._ck(self._lib.gpp_dist_init(self._h, int(rank), int(world), buf), "gpp_dist_init")
         self.rank, self.world = int(rank), int(world)
+
+    def dist_init_virtual(self, nranks):
+        """Tests: run the task plans of `nranks` ranks one after the other on this GPU (no NCCL)."""
+        self._ck(self._lib.gpp_dist_init_virtual(self._h, int(nranks)), "gpp_dist_init_virtual")
+        self.rank, self.world = 0, int(nranks)
+
+    def dist_set_grid(self, P, Q):
+        self._ck(self._lib.gpp_dist_set_grid(self._h, int(P), int(Q)), "gpp_dist_set_grid")
+
+    def dist_info(self):
+        v = [C.c_int() for _ in range(4)]
+        self._ck(self._lib.gpp_dist_info(self._h, *[C.byref(x) for x in v]), "gpp_dist_info")
+        return dict(zip(("rank", "world", "P", "Q"), (x.value for x in v)))
 
     def dist_finalize(self):
         self._ck(self._lib.gpp_dist_finalize(self._h), "gpp_dist_finalize")
@@ -325,19 +341,14 @@ class Engine:
         kp = kernel_params(kernel, kernel_parameter)
         self._ck(self._lib.gpp_dist_gram_assemble(self._h, LAYOUT[layout], KERNEL[kernel], _ptr(kp)), "gpp_dist_gram_assemble")
 
-    def dist_local_rows(self):
-        n, M = C.c_int(), C.c_int()
-        self._ck(self._lib.gpp_dist_local_rows(self._h, C.byref(n), C.byref(M)), "gpp_dist_local_rows")
-        return n.value, M.value
-
     def dist_get_diag(self):
-        _, M = self.dist_local_rows()
+        M, _ = self.gram_size(0)
         out = np.empty(M)
         self._ck(self._lib.gpp_dist_get_diag(self._h, _ptr(out)), "gpp_dist_get_diag")
         return out
 
     def dist_add_diag(self, add):
-        _, M = self.dist_local_rows()
+        M, _ = self.gram_size(0)
         add = _f64(add, (M,))
         self._ck(self._lib.gpp_dist_add_diag(self._h, _ptr(add)), "gpp_dist_add_diag")
 
@@ -346,11 +357,13 @@ class Engine:
         self._ck(self._lib.gpp_dist_potrf(self._h, C.byref(info)), "gpp_dist_potrf")
         return info.value
 
-    def dist_download_local(self):
-        n, M = self.dist_local_rows()
-        out = np.empty((n, M))
-        self._ck(self._lib.gpp_dist_download_local(self._h, _ptr(out)), "gpp_dist_download_local")
-        return out
+    def dist_inverse(self):
+        self._ck(self._lib.gpp_dist_inverse(self._h), "gpp_dist_inverse")
+
+    def dist_gn_step(self, step):
+        v = C.c_double()
+        self._ck(self._lib.gpp_dist_gn_step(self._h, float(step), C.byref(v)), "gpp_dist_gn_step")
+        return float(v.value)
 
 
 def nccl_unique_id():

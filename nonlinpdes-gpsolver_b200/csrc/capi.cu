@@ -61,6 +61,33 @@ bool bad_slot(gpp_handle* h, int slot, bool need_T = true) {
 
 }  // namespace
 
+int gram_slot_prepare(gpp_handle* h, int slot, int layout, int kernel, const double* kparams) {
+  if (bad_slot(h, slot, false)) return -2;
+  if (!h->Xall) { h->err = "points not set"; return -1; }
+  if (layout < 0 || layout > 3) { h->err = "bad layout"; return -3; }
+  if (kernel < 0 || kernel > 1) { h->err = "bad kernel"; return -4; }
+  if (!kparams) { h->err = "kparams missing"; return -5; }
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  GramSlot& s = h->slot[slot];
+  s.layout_id = layout;
+  s.lay = make_layout(layout);
+  s.N = h->N; s.Nb = (layout == LAY_DARCY_A) ? 0 : h->Nb;
+  int o = 0;
+  for (int p = 0; p < s.lay.nblk; ++p) { s.off[p] = o; o += s.N + (s.lay.with_bdy[p] ? s.Nb : 0); }
+  s.off[s.lay.nblk] = o;
+  s.M = o; s.ld = round_up(s.M, 16);
+  int rc = dev_alloc(h, &s.T, (size_t)s.M * s.ld);
+  if (rc) return rc;
+  rc = make_tensor_map(h, &s.mapT, s.T, s.M, s.M, s.ld);     // host-side encode only; M / ld may have changed
+  if (rc) return rc;
+  s.Mint = s.lay.nblk * s.N;
+  s.kernel_id = kernel;
+  s.kp_b1 = kparams[0]; s.kp_b2 = kparams[1]; s.kp_e1 = kparams[2]; s.kp_e2 = kparams[3];
+  s.factored = s.inverted = false;
+  h->dist_gn = false;
+  return GPP_OK;
+}
+
 extern "C" {
 
 int gpp_create(int device, gpp_handle** out) {
@@ -198,31 +225,9 @@ int gpp_set_points(gpp_handle* h, const double* Xd, int N, const double* Xb, int
 int gpp_gram_assemble(gpp_handle* h, int slot, int layout, int kernel, const double* kparams) {
   NvtxRange nvtx_range("gpp:gram_assemble");
   if (h) cudaSetDevice(h->device);
-  if (bad_slot(h, slot, false)) return -2;
-  if (!h->Xall) { h->err = "points not set"; return -1; }
-  if (layout < 0 || layout > 3) { h->err = "bad layout"; return -3; }
-  if (kernel < 0 || kernel > 1) { h->err = "bad kernel"; return -4; }
-  if (!kparams) { h->err = "kparams missing"; return -5; }
-  CUDA_TRY(h, cudaSetDevice(h->device));
-  GramSlot& s = h->slot[slot];
-  s.layout_id = layout;
-  s.lay = make_layout(layout);
-  s.N = h->N; s.Nb = (layout == LAY_DARCY_A) ? 0 : h->Nb;
-  int o = 0;
-  for (int p = 0; p < s.lay.nblk; ++p) { s.off[p] = o; o += s.N + (s.lay.with_bdy[p] ? s.Nb : 0); }
-  s.off[s.lay.nblk] = o;
-  s.M = o; s.ld = round_up(s.M, 16);
-  {
-    int rc = dev_alloc(h, &s.T, (size_t)s.M * s.ld);
-    if (rc) return rc;
-    rc = make_tensor_map(h, &s.mapT, s.T, s.M, s.M, s.ld);     // host-side encode only; M / ld may have changed
-    if (rc) return rc;
-  }
-  s.Mint = s.lay.nblk * s.N;
-  s.kernel_id = kernel;
-  s.kp_b1 = kparams[0]; s.kp_b2 = kparams[1]; s.kp_e1 = kparams[2]; s.kp_e2 = kparams[3];
-  s.factored = s.inverted = false;
-  return gram_assemble(h, s);
+  int rc = gram_slot_prepare(h, slot, layout, kernel, kparams);
+  if (rc) return rc;
+  return gram_assemble(h, h->slot[slot]);
 }
 
 int gpp_gram_size(gpp_handle* h, int slot, int* M, int* Mint) {

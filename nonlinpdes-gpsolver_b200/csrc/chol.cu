@@ -17,74 +17,104 @@ constexpr int BASE = 64;
 constexpr int LDS_PAD = BASE + 1;
 
 // ---------------------------------------------------------------------------
-// potrf of one diagonal block (n <= 64) held in shared memory: one thread per row, left-looking,
-// each entry reduced progressively in column order (same rounding model as the GEMM updates).
+// potrf of one diagonal block (n <= 64): one thread per row, the row lives in registers.
+// Right-looking over columns j = 0..63 (fully unrolled): thread j publishes sqrt(a_jj), every thread i > j
+// publishes l_ij = a_ij / l_jj, then a_ik -= l_ij l_kj for k > j.  Entry (i, k) therefore receives its updates
+// one by one in column order, each rounded relative to the remainder (same rounding model as the GEMM
+// updates -- and the same operation sequence as a left-looking dot product started at a_ik).
 // A non-positive / NaN pivot is recorded once in *info (1-based global index);
 // sqrt then produces NaN which propagates, like jnp.linalg.cholesky's NaN output.
+// Blocks with n < 64 are padded with the identity.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(BASE)
 potrf_base_kernel(double* __restrict__ A, long ld, int n, int gidx0, int* info) {
-  __shared__ double s[BASE * LDS_PAD];
-  const int i = threadIdx.x;          // one thread per row
+  __shared__ double stage[BASE * LDS_PAD];
+  __shared__ double col[BASE];
+  __shared__ double sdiag;
+  const int i = threadIdx.x;
   for (int r = 0; r < n; ++r)         // coalesced row loads
-    if (i <= r) s[r * LDS_PAD + i] = A[(long)r * ld + i];
+    if (i <= r) stage[r * LDS_PAD + i] = A[(long)r * ld + i];
   __syncthreads();
-  for (int j = 0; j < n; ++j) {
-    // left-looking, progressive: acc starts at a_ij and is reduced term by term in column order
-    double acc = 0.0;
-    if (i >= j && i < n) {
-      acc = s[i * LDS_PAD + j];
-      const double* ri = s + i * LDS_PAD;
-      const double* rj = s + j * LDS_PAD;
-      for (int k = 0; k < j; ++k) acc = fma(-ri[k], rj[k], acc);
-      if (i == j) {
-        if (!(acc > 0.0)) atomicCAS(info, 0, gidx0 + j + 1);
-        s[j * LDS_PAD + j] = sqrt(acc);
-      }
+  double a[BASE];
+#pragma unroll
+  for (int k = 0; k < BASE; ++k) a[k] = (i < n && k <= i) ? stage[i * LDS_PAD + k] : (k == i ? 1.0 : 0.0);
+#pragma unroll
+  for (int j = 0; j < BASE; ++j) {
+    if (i == j) {
+      const double d = a[j];
+      if (!(d > 0.0) && j < n) atomicCAS(info, 0, gidx0 + j + 1);
+      const double sq = sqrt(d);
+      a[j] = sq;
+      sdiag = sq;
     }
     __syncthreads();
-    if (i > j && i < n) s[i * LDS_PAD + j] = acc / s[j * LDS_PAD + j];
+    double l = 0.0;
+    if (i > j) { l = a[j] / sdiag; a[j] = l; }
+    col[i] = l;
     __syncthreads();
+#pragma unroll
+    for (int k = j + 1; k < BASE; ++k) a[k] = fma(-l, col[k], a[k]);   // entries k > i are never read
   }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < BASE; ++k) stage[i * LDS_PAD + k] = a[k];
+  __syncthreads();
   for (int r = 0; r < n; ++r)
-    if (i <= r) A[(long)r * ld + i] = s[r * LDS_PAD + i];
+    if (i <= r) A[(long)r * ld + i] = stage[r * LDS_PAD + i];
 }
 
 // ---------------------------------------------------------------------------
 // X * L^T = P  for an nb x nb (nb <= 64) lower-triangular L, P is rows x nb, in place.
-// One thread per row, substitution along the row:  x_j = (p_j - sum_{k<j} x_k L_jk) / L_jj.
+// One thread per row, the row lives in registers; substitution along the row, right-looking and fully unrolled:
+//   x_j = p_j / L_jj, then p_k -= x_j L_kj for k > j   (the same operation sequence per entry as
+//   x_j = (p_j - sum_{k<j} x_k L_jk) / L_jj evaluated term by term).
+// L is held transposed in shared memory (a column of L is contiguous: broadcast 128-bit loads); it is padded
+// with the identity for nb < 64.  blockIdx.x -> 128 rows: rows are either contiguous (row_stride_blk == 0) or
+// block-cyclic: logical row block b of row_nb rows sits at physical rows (row_first_blk + b * row_stride_blk) * row_nb.
 // ---------------------------------------------------------------------------
 constexpr int TRSM_ROWS = 128;
+__device__ __forceinline__ long trsm_phys_row(const TrsmRows& m, int r) {
+  if (m.stride_blk == 0) return r;
+  return (long)(m.first_blk + (r / m.nb) * m.stride_blk) * m.nb + r % m.nb;
+}
 __global__ void __launch_bounds__(TRSM_ROWS)
-trsm_base_kernel(double* __restrict__ P, long ldp, int rows, const double* __restrict__ L, long ldl, int nb) {
+trsm_base_kernel(double* __restrict__ P, long ldp, const TrsmRows rm, const double* __restrict__ L, long ldl, int nb) {
   extern __shared__ double sm[];
-  double* sL = sm;                       // nb x LDS_PAD
-  double* sP = sm + BASE * LDS_PAD;      // TRSM_ROWS x LDS_PAD
+  double* sLt = sm;                      // [64][64] transposed: sLt[j * 64 + k] = L[k][j]
+  double* sP = sm + BASE * BASE;         // TRSM_ROWS x LDS_PAD
   const int tid = threadIdx.x;
   const int r0 = blockIdx.x * TRSM_ROWS;
-  for (int e = tid; e < nb * nb; e += blockDim.x) {
-    int i = e / nb, j = e % nb;
-    sL[i * LDS_PAD + j] = (j <= i) ? L[(long)i * ldl + j] : 0.0;
+  for (int e = tid; e < BASE * BASE; e += blockDim.x) {
+    const int k = e / BASE, j = e % BASE;          // L[k][j], coalesced over j
+    double v = (k == j) ? 1.0 : 0.0;
+    if (k < nb && j < nb) v = (j <= k) ? L[(long)k * ldl + j] : 0.0;
+    sLt[j * BASE + k] = v;
   }
-  const int nrow = min(TRSM_ROWS, rows - r0);
+  const int nrow = min(TRSM_ROWS, rm.rows - r0);
   for (int e = tid; e < nrow * nb; e += blockDim.x) {
-    int i = e / nb, j = e % nb;
-    sP[i * LDS_PAD + j] = P[(long)(r0 + i) * ldp + j];
+    const int i = e / nb, j = e % nb;
+    sP[i * LDS_PAD + j] = P[trsm_phys_row(rm, r0 + i) * ldp + j];
   }
   __syncthreads();
   if (tid < nrow) {
-    double* x = sP + tid * LDS_PAD;
-    for (int j = 0; j < nb; ++j) {
-      double acc = x[j];
-      const double* lj = sL + j * LDS_PAD;
-      for (int k = 0; k < j; ++k) acc = fma(-x[k], lj[k], acc);
-      x[j] = acc / lj[j];
+    double x[BASE];
+#pragma unroll
+    for (int k = 0; k < BASE; ++k) x[k] = (k < nb) ? sP[tid * LDS_PAD + k] : 0.0;
+#pragma unroll
+    for (int j = 0; j < BASE; ++j) {
+      const double* lc = sLt + j * BASE;
+      const double xj = x[j] / lc[j];
+      x[j] = xj;
+#pragma unroll
+      for (int k = j + 1; k < BASE; ++k) x[k] = fma(-xj, lc[k], x[k]);
     }
+#pragma unroll
+    for (int k = 0; k < BASE; ++k) if (k < nb) sP[tid * LDS_PAD + k] = x[k];
   }
   __syncthreads();
   for (int e = tid; e < nrow * nb; e += blockDim.x) {
-    int i = e / nb, j = e % nb;
-    P[(long)(r0 + i) * ldp + j] = sP[i * LDS_PAD + j];
+    const int i = e / nb, j = e % nb;
+    P[trsm_phys_row(rm, r0 + i) * ldp + j] = sP[i * LDS_PAD + j];
   }
 }
 
@@ -184,20 +214,34 @@ trsv_bwd_update_kernel(const double* __restrict__ Lrows, long ld, int cols, int 
 
 }  // namespace
 
+int trsm_base_launch(gpp_handle* h, double* P, long ldp, const TrsmRows& rm, const double* L, long ldl, int nbl) {
+  if (rm.rows <= 0 || nbl <= 0) return GPP_OK;
+  static bool attr[64] = {false};        // function attributes are per device
+  const int smem = (BASE * BASE + TRSM_ROWS * LDS_PAD) * 8;
+  if (h->device >= 64 || !attr[h->device]) {
+    CUDA_TRY(h, cudaFuncSetAttribute(trsm_base_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (h->device < 64) attr[h->device] = true;
+  }
+  trsm_base_kernel<<<(rm.rows + TRSM_ROWS - 1) / TRSM_ROWS, TRSM_ROWS, smem, h->cur>>>(P, ldp, rm, L, ldl, nbl);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return GPP_OK;
+}
+
+int fill_identity_launch(gpp_handle* h, double* A, long ld, int rows, int cols) {
+  const long tot = (long)rows * cols;
+  if (tot <= 0) return GPP_OK;
+  fill_identity_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->cur>>>(A, ld, rows, cols);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return GPP_OK;
+}
+
 int trsm_right_lt(gpp_handle* h, const Mat& P, int pr0, int pc0, int rows, const Mat& L, int lr0, int lc0, int nb) {
   if (rows <= 0 || nb <= 0) return GPP_OK;
   if (nb <= BASE) {
-    static bool attr[64] = {false};        // function attributes are per device
-    const int smem = (BASE * LDS_PAD + TRSM_ROWS * LDS_PAD) * 8;
-    if (h->device >= 64 || !attr[h->device]) {
-      CUDA_TRY(h, cudaFuncSetAttribute(trsm_base_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      if (h->device < 64) attr[h->device] = true;
-    }
-    trsm_base_kernel<<<(rows + TRSM_ROWS - 1) / TRSM_ROWS, TRSM_ROWS, smem, h->cur>>>(
-        P.base + (long)pr0 * P.ld + pc0, P.ld, rows, L.base + (long)lr0 * L.ld + lc0, L.ld, nb);
-    h->launches++;
-    CUDA_TRY(h, cudaGetLastError());
-    return GPP_OK;
+    TrsmRows rm{rows, 0, 0, 0};
+    return trsm_base_launch(h, P.base + (long)pr0 * P.ld + pc0, P.ld, rm, L.base + (long)lr0 * L.ld + lc0, L.ld, nb);
   }
   const int hh = (int)round_up((nb + 1) / 2, BASE);
   int rc = trsm_right_lt(h, P, pr0, pc0, rows, L, lr0, lc0, hh);

@@ -1,35 +1,83 @@
-// Multi-GPU path: one process per GPU, block rows of Theta dealt cyclically to the ranks
-// (a P x 1 process grid of the 2-D block-cyclic family), NCCL over NVLink for the one exchange per
-// block column.  The reference has no multi-device code at all: this is new.
+// Multi-GPU path: ONE problem sharded over the GPUs of a box.  One process per GPU, NCCL over NVLink / NVSwitch.
+// The reference has no multi-device code at all: this is new.
 //
-//   assembly : every Gram entry depends on two points only -> each rank fills the block rows it owns
-//              (gram_assemble_rows), no exchange.
-//   Cholesky : left-looking by block column j.  The owner of block row j brings its diagonal block up to
-//              date, factorises it, and broadcasts the finished block row L[j, 0:(j+1)NB] (ncclBroadcast);
-//              every rank then updates and solves its own block rows below j with the same DMMA GEMM and
-//              substitution kernels as the single-GPU path.  Work per step is ~ (#block rows below j) / P.
+// Storage is REPLICATED, work is OWNER-COMPUTES.  Every rank holds the full M x ld buffer of Theta -> L (and of
+// U = L^{-T}, and of the GN Hessian H); block (bi, bc) of NB x NB is owned by rank (bi mod P) * Q + (bc mod Q) of a
+// P x Q process grid (2-D block-cyclic; Q = 1, the default, is block-row cyclic).  Only the owner updates a block;
+// a block column that has become final is made consistent on every rank by one gather.  With NVSwitch every rank
+// receives a panel at full link bandwidth whatever the grid shape, and 180 GB of HBM hold the replicated buffers at
+// N_domain = 40 000 (52 GB each), so the classic reason for 2-D grids (panel volume per rank) does not apply; what
+// does matter is the per-column critical path, and the right-looking schedule below keeps it short:
+//
+//   assembly : every Gram entry depends on two points only -> each rank fills the block rows it holds, no exchange.
+//   Cholesky : right-looking by block column j.  owner(j, j) factorises the diagonal block and broadcasts it; the
+//              owners of the panel blocks (bi, j) solve them against it (block-cyclic rows: all P process rows work);
+//              the solved panel is gathered on every rank; every rank applies C(bi, bc) -= L(bi, j) L(bc, j)^T to the
+//              trailing blocks it owns in ONE task-list launch of the DMMA kernel (K = NB, thousands of tiles, so wave
+//              quantisation is negligible).  Look-ahead: column j+1 is updated first and its panel chain (diagonal
+//              factorisation, broadcast, solve, gather) runs on a high-priority stream under the bulk of step j.
+//              Each entry receives its updates in column order, each rounded relative to the remainder: the same
+//              progressive accumulation as the single-GPU factorisation.
+//   U = L^-T : same skeleton on a second, clean buffer (zeros below the diagonal): at step i the owners solve
+//              column i (U(b, i) L_ii^T = acc(b, i)), then update acc(b, c) -= U(b, i) L(c, i)^T for c > i.  L is
+//              replicated, so for Q = 1 this needs no exchange on the critical path; the finished columns are
+//              gathered on a third stream because every rank needs all of U next.
+//   A blocks : the GN Hessian block (bi, bc) needs the four sub-blocks A_pp'(bi, bc) of the interior inverse
+//              A = (U U^T)[interior]; their owner computes exactly those (one task-list launch, K from the diagonal to M).
+//   GN step  : z, F, the triangular solves with L and the gradient are replicated (identical on every rank); the
+//              Hessian blocks are assembled by their owners and H is factorised by the same distributed Cholesky.
+//
+// "Virtual" mode (gpp_dist_init_virtual) runs the same plans for all P*Q ranks one after the other on a single GPU,
+// without NCCL: it lets the single-GPU test suite check ownership, task lists and kernels of the sharded path.
 #include "../../include/gpp.h"
 #include "gpp_internal.cuh"
 
 #include <nccl.h>
 
+#include <algorithm>
 #include <cstring>
+#include <map>
 #include <vector>
 
 namespace {
 
+struct Grid { int P, Q, p, q; };
+inline int owner_of(const Grid& g, int bi, int bc) { return (bi % g.P) * g.Q + (bc % g.Q); }
+inline bool mine(const Grid& g, int bi, int bc) { return bi % g.P == g.p && bc % g.Q == g.q; }
+
+struct Launch { size_t off = 0; int count = 0; };
+
+// Task lists of one phase for one (virtual) rank; built once per (size, NB, grid) and kept on the device.
+struct Plan {
+  long key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  bool valid = false;
+  std::vector<GemmTask> host;
+  GemmTask* dev = nullptr;
+  size_t dev_cap = 0;
+  std::vector<Launch> la, bulkA, bulkB;           // per step
+  std::vector<std::vector<Launch>> trsm;          // per step: GEMMs of the panel-solve recursion, in execution order
+  std::vector<TrsmRows> rows;                     // per step: (block-cyclic) rows of the panel solve
+  std::vector<int4> hblocks;                      // A phase: own Hessian blocks {bi, bc, e, 0}
+  int4* dev_hblocks = nullptr;
+  size_t dev_hblocks_cap = 0;
+  Launch all;                                     // A phase: the single launch
+};
+
 struct DistState {
   ncclComm_t comm = nullptr;
-  int rank = 0, world = 1;
-  // row-sharded Theta / L of slot 0
-  double* Tloc = nullptr;
-  long ld = 0;
-  int M = 0, nloc = 0;          // global size, local row count
-  TMap2 mapLoc;
-  double* rowbuf = nullptr;     // NB x M staging of the broadcast block row (two buffers alternate)
-  double* rowbuf2 = nullptr;
-  double* dvec = nullptr;       // M doubles scratch
-  bool factored = false;
+  int rank = 0, world = 1;       // NCCL rank / size (world == 1 in virtual mode)
+  int nv = 0;                    // > 0: virtual mode, nv ranks emulated on this GPU
+  int P = 1, Q = 1;
+  double* U = nullptr;           // M x ld, U = L^{-T} (clean: zeros below the diagonal)
+  TMap2 mapU;
+  double* Asub = nullptr;        // own sub-blocks of the interior inverse, NBH x NBH each
+  int nbh = 0;
+  double* gbuf = nullptr;        // panel gather staging
+  double* dbuf = nullptr;        // diagonal-block staging
+  double* dvec = nullptr;        // M doubles
+  cudaStream_t sC = nullptr;     // communication stream of the U phase
+  std::map<int, Plan> plans;     // key: phase * 4096 + virtual rank
+  bool inverse_ready = false;
 };
 
 DistState* ds(gpp_handle* h) { return static_cast<DistState*>(h->dist); }
@@ -43,22 +91,580 @@ DistState* ds(gpp_handle* h) { return static_cast<DistState*>(h->dist); }
     }                                                                          \
   } while (0)
 
-// block row b (global) -> owner, local block index
-inline int owner_of(int b, int P) { return b % P; }
-inline int local_blk(int b, int P) { return b / P; }
-// number of block rows <= j owned by rank
-inline int owned_upto(int j, int rank, int P) { return j >= rank ? (j - rank) / P + 1 : 0; }
+inline int nblocks_of(int n, int NB) { return (n + NB - 1) / NB; }
+inline int rows_of(int n, int NB, int b) { return (n - b * NB < NB) ? (n - b * NB) : NB; }
 
-__global__ void dist_get_diag_kernel(const double* __restrict__ T, long ld, int lrow0, int g0, int nrows, double* __restrict__ out) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < nrows) out[g0 + i] = T[(long)(lrow0 + i) * ld + g0 + i];
+std::vector<Grid> grids_of(const DistState* d) {
+  std::vector<Grid> v;
+  if (d->nv > 0) {
+    for (int r = 0; r < d->nv; ++r) v.push_back(Grid{d->P, d->Q, r / d->Q, r % d->Q});
+  } else {
+    v.push_back(Grid{d->P, d->Q, d->rank / d->Q, d->rank % d->Q});
+  }
+  return v;
 }
-__global__ void dist_add_diag_kernel(double* __restrict__ T, long ld, int lrow0, int g0, int nrows, const double* __restrict__ add) {
+
+struct EventPool {
+  gpp_handle* h;
+  size_t used = 0;
+  explicit EventPool(gpp_handle* hh) : h(hh) {}
+  cudaEvent_t get() {
+    if (used == h->evpool.size()) {
+      cudaEvent_t e;
+      cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+      h->evpool.push_back(e);
+    }
+    return h->evpool[used++];
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// small kernels
+// ---------------------------------------------------------------------------------------------------------
+__global__ void dist_get_diag_kernel(const double* __restrict__ T, long ld, int g0, int nrows, double* __restrict__ out) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < nrows) T[(long)(lrow0 + i) * ld + g0 + i] += add[g0 + i];
+  if (i < nrows) out[g0 + i] = T[(long)(g0 + i) * ld + g0 + i];
+}
+__global__ void dist_add_diag_kernel(double* __restrict__ T, long ld, int g0, int nrows, const double* __restrict__ add) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nrows) T[(long)(g0 + i) * ld + g0 + i] += add[g0 + i];
+}
+
+// Panel staging.  Blocks (b, col), b in [b_lo, b_hi), of a replicated matrix X; the blocks of process row pr
+// (b mod P == pr, ascending) occupy slots pr * cnt_max + t of the staging buffer, NB * NB doubles each, rows of w doubles.
+struct PanelGeom {
+  int NB, n, col0, w;        // block size, matrix size, first column of the panel, panel width
+  int b_lo, b_hi, P, cnt_max;
+};
+__device__ __forceinline__ int panel_slot(const PanelGeom& g, int b) {
+  const int pr = b % g.P;
+  int first = g.b_lo + ((pr - g.b_lo % g.P) + g.P) % g.P;       // smallest b' >= b_lo with b' mod P == pr
+  return pr * g.cnt_max + (b - first) / g.P;
+}
+// grid: (blocks to copy, NB / 8); 256 threads.  mode 0: pack blocks of process row `pr_sel`; mode 1: unpack all blocks
+// except those of (pr_skip) when skip >= 0
+__global__ void __launch_bounds__(256)
+panel_copy_kernel(double* __restrict__ X, long ld, double* __restrict__ buf, const PanelGeom g, int mode, int pr_sel) {
+  int b;
+  if (mode == 0) {
+    int first = g.b_lo + ((pr_sel - g.b_lo % g.P) + g.P) % g.P;
+    b = first + blockIdx.x * g.P;
+  } else {
+    b = g.b_lo + blockIdx.x;
+    if (pr_sel >= 0 && b % g.P == pr_sel) return;
+  }
+  if (b >= g.b_hi) return;
+  const int rows = (g.n - b * g.NB < g.NB) ? (g.n - b * g.NB) : g.NB;
+  double* sb = buf + (long)panel_slot(g, b) * g.NB * g.NB;
+  for (int r = blockIdx.y * 8 + (threadIdx.x >> 5); r < rows; r += gridDim.y * 8) {
+    double* xr = X + (long)(b * g.NB + r) * ld + g.col0;
+    double* br = sb + (long)r * g.w;
+    for (int c = threadIdx.x & 31; c < g.w; c += 32) {
+      if (mode == 0) br[c] = xr[c];
+      else xr[c] = br[c];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// plans
+// ---------------------------------------------------------------------------------------------------------
+Plan& plan_slot(DistState* d, int phase, int vr) { return d->plans[phase * 4096 + vr]; }
+
+bool plan_matches(Plan& pl, const long* key) {
+  if (!pl.valid) return false;
+  for (int k = 0; k < 8; ++k) if (pl.key[k] != key[k]) return false;
+  return true;
+}
+
+void plan_reset(Plan& pl, const long* key) {
+  for (int k = 0; k < 8; ++k) pl.key[k] = key[k];
+  pl.host.clear(); pl.la.clear(); pl.bulkA.clear(); pl.bulkB.clear(); pl.trsm.clear(); pl.rows.clear(); pl.hblocks.clear();
+  pl.all = Launch{};
+  pl.valid = false;
+}
+
+int plan_upload(gpp_handle* h, Plan& pl) {
+  if (pl.host.size() > pl.dev_cap) {
+    if (pl.dev) cudaFree(pl.dev);
+    pl.dev = nullptr;
+    pl.dev_cap = pl.host.size() + pl.host.size() / 8 + 16;
+    CUDA_TRY(h, cudaMalloc(&pl.dev, pl.dev_cap * sizeof(GemmTask)));
+  }
+  if (!pl.host.empty())
+    CUDA_TRY(h, cudaMemcpyAsync(pl.dev, pl.host.data(), pl.host.size() * sizeof(GemmTask), cudaMemcpyHostToDevice, h->stream));
+  if (pl.hblocks.size() > pl.dev_hblocks_cap) {
+    if (pl.dev_hblocks) cudaFree(pl.dev_hblocks);
+    pl.dev_hblocks = nullptr;
+    pl.dev_hblocks_cap = pl.hblocks.size() + 16;
+    CUDA_TRY(h, cudaMalloc(&pl.dev_hblocks, pl.dev_hblocks_cap * sizeof(int4)));
+  }
+  if (!pl.hblocks.empty())
+    CUDA_TRY(h, cudaMemcpyAsync(pl.dev_hblocks, pl.hblocks.data(), pl.hblocks.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));     // the host vectors may be rebuilt later
+  pl.valid = true;
+  return GPP_OK;
+}
+
+GemmTask make_task(int a_row, int b_row, int c_row, int c_col, int m, int n, int k0, int k1, int kb_off, int tri) {
+  GemmTask t{};
+  t.a_row = a_row; t.b_row = b_row; t.c_row = c_row; t.c_col = c_col;
+  t.m = m; t.n = n; t.k0 = k0; t.k1 = k1; t.kb_off = kb_off; t.tri = tri;
+  return t;
+}
+
+// GEMMs of the recursive panel solve X L^T = P (mirrors trsm_right_lt in chol.cu) over the row blocks `blks`
+// (physical block indices, `brows` rows each); panel columns [pc0, pc0 + nb), L block at (lr0, lc0) of the L operand.
+void plan_trsm(Plan& pl, std::vector<Launch>& out, const std::vector<int>& blks, const std::vector<int>& brows, int NB,
+               int pc0, int lr0, int lc0, int nb) {
+  if (nb <= 64 || blks.empty()) return;
+  const int hh = (int)round_up((nb + 1) / 2, 64);
+  plan_trsm(pl, out, blks, brows, NB, pc0, lr0, lc0, hh);
+  Launch l;
+  l.off = pl.host.size(); l.count = (int)blks.size();
+  for (size_t t = 0; t < blks.size(); ++t)
+    pl.host.push_back(make_task(blks[t] * NB, lr0 + hh, blks[t] * NB, pc0 + hh, brows[t], nb - hh, pc0, pc0 + hh, lc0 - pc0, 0));
+  out.push_back(l);
+  plan_trsm(pl, out, blks, brows, NB, pc0 + hh, lr0 + hh, lc0 + hh, nb - hh);
+}
+
+TrsmRows rows_of_blocks(const std::vector<int>& blks, const std::vector<int>& brows, int NB, int stride) {
+  TrsmRows r{0, 0, 0, NB};
+  if (blks.empty()) return r;
+  r.first_blk = blks[0];
+  r.stride_blk = stride;
+  r.rows = (int)(blks.size() - 1) * NB + brows.back();
+  return r;
+}
+
+// right-looking Cholesky of an n x n matrix, block size NB, for the rank at g
+void build_potrf_plan(Plan& pl, const Grid& g, int n, int NB) {
+  const int nblk = nblocks_of(n, NB);
+  pl.la.assign(nblk, Launch{}); pl.bulkA.assign(nblk, Launch{}); pl.bulkB.assign(nblk, Launch{});
+  pl.trsm.assign(nblk, {}); pl.rows.assign(nblk, TrsmRows{0, 0, 0, NB});
+  for (int j = 0; j < nblk; ++j) {
+    const int j0 = j * NB, nbj = rows_of(n, NB, j);
+    std::vector<int> blks, brows;
+    if (j % g.Q == g.q)
+      for (int bi = j + 1; bi < nblk; ++bi)
+        if (bi % g.P == g.p) { blks.push_back(bi); brows.push_back(rows_of(n, NB, bi)); }
+    pl.rows[j] = rows_of_blocks(blks, brows, NB, g.P);
+    plan_trsm(pl, pl.trsm[j], blks, brows, NB, j0, j0, j0, nbj);
+    auto emit = [&](Launch& l, int c_lo, int c_hi) {       // own blocks (bi, bc), c_lo <= bc < c_hi, bc <= bi
+      l.off = pl.host.size();
+      for (int bc = c_lo; bc < c_hi && bc < nblk; ++bc)
+        for (int bi = bc; bi < nblk; ++bi)
+          if (mine(g, bi, bc))
+            pl.host.push_back(make_task(bi * NB, bc * NB, bi * NB, bc * NB, rows_of(n, NB, bi), rows_of(n, NB, bc), j0, j0 + nbj, 0, bi == bc));
+      l.count = (int)(pl.host.size() - l.off);
+    };
+    emit(pl.la[j], j + 1, j + 2);
+    emit(pl.bulkA[j], j + 2, j + 3);
+    emit(pl.bulkB[j], j + 3, nblk);
+  }
+}
+
+// U = L^{-T}: at step i the blocks (b, i), b <= i, are solved; then (b, c), b <= i < c, receive -U(b, i) L(c, i)^T
+void build_uinv_plan(Plan& pl, const Grid& g, int n, int NB) {
+  const int nblk = nblocks_of(n, NB);
+  pl.la.assign(nblk, Launch{}); pl.bulkA.assign(nblk, Launch{}); pl.bulkB.assign(nblk, Launch{});
+  pl.trsm.assign(nblk, {}); pl.rows.assign(nblk, TrsmRows{0, 0, 0, NB});
+  for (int i = 0; i < nblk; ++i) {
+    const int i0 = i * NB, nbi = rows_of(n, NB, i);
+    std::vector<int> blks, brows;
+    if (i % g.Q == g.q)
+      for (int b = 0; b <= i; ++b)
+        if (b % g.P == g.p) { blks.push_back(b); brows.push_back(rows_of(n, NB, b)); }
+    pl.rows[i] = rows_of_blocks(blks, brows, NB, g.P);
+    plan_trsm(pl, pl.trsm[i], blks, brows, NB, i0, i0, i0, nbi);
+    auto emit = [&](Launch& l, int c_lo, int c_hi) {
+      l.off = pl.host.size();
+      for (int c = c_lo; c < c_hi && c < nblk; ++c)
+        for (int b = 0; b <= i; ++b)
+          if (mine(g, b, c))
+            pl.host.push_back(make_task(b * NB, c * NB, b * NB, c * NB, rows_of(n, NB, b), rows_of(n, NB, c), i0, i0 + nbi, 0, 0));
+      l.count = (int)(pl.host.size() - l.off);
+    };
+    emit(pl.la[i], i + 1, i + 2);
+    emit(pl.bulkA[i], i + 2, i + 3);
+    emit(pl.bulkB[i], i + 3, nblk);
+  }
+}
+
+// sub-blocks of the interior inverse needed by the own Hessian blocks (elliptic layout: 2 operator blocks, H is N x N)
+void build_ablock_plan(Plan& pl, const Grid& g, int N, int M, const int* off, int nbh) {
+  const int nblk = nblocks_of(N, nbh);
+  for (int bi = 0; bi < nblk; ++bi)
+    for (int bc = 0; bc <= bi; ++bc)
+      if (mine(g, bi, bc)) pl.hblocks.push_back(make_int4(bi, bc, (int)pl.hblocks.size(), 0));
+  pl.all.off = 0;
+  const int k1 = (int)round_up(M, 16);
+  for (const int4& hb : pl.hblocks)
+    for (int p = 0; p < 2; ++p)
+      for (int pp = 0; pp < 2; ++pp) {
+        const int a_row = off[p] + hb.x * nbh, b_row = off[pp] + hb.y * nbh;
+        const int k0 = (std::max(a_row, b_row) / 16) * 16;
+        pl.host.push_back(make_task(a_row, b_row, (hb.z * 4 + p * 2 + pp) * nbh, 0, rows_of(N, nbh, hb.x), rows_of(N, nbh, hb.y), k0, k1, 0, 0));
+      }
+  // longest K first: the hardware scheduler then balances the variable-length tiles
+  std::stable_sort(pl.host.begin(), pl.host.end(), [](const GemmTask& a, const GemmTask& b) { return (a.k1 - a.k0) > (b.k1 - b.k0); });
+  pl.all.count = (int)pl.host.size();
+}
+
+int ensure_plan(gpp_handle* h, DistState* d, int phase, int vr, const Grid& g, int n, int NB, int extraM, const int* off, Plan** out) {
+  Plan& pl = plan_slot(d, phase, vr);
+  const long key[8] = {phase, n, NB, g.P, g.Q, g.p * 65536L + g.q, extraM, off ? off[1] : 0};
+  if (!plan_matches(pl, key)) {
+    plan_reset(pl, key);
+    if (phase == 0 || phase == 3) build_potrf_plan(pl, g, n, NB);
+    else if (phase == 1) build_uinv_plan(pl, g, n, NB);
+    else build_ablock_plan(pl, g, n, extraM, off, NB);
+    int rc = plan_upload(h, pl);
+    if (rc) return rc;
+  }
+  *out = &pl;
+  return GPP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// execution helpers (all on h->cur)
+// ---------------------------------------------------------------------------------------------------------
+struct MatRef { double* base; long ld; const TMap2* map; };
+
+int run_tasks(gpp_handle* h, const Plan& pl, const Launch& l, const MatRef& A, const MatRef& B, const MatRef& C, int bs, double alpha, bool accumulate) {
+  if (l.count <= 0) return GPP_OK;
+  GemmTaskDesc d{};
+  d.mapA = A.map; d.mapB = B.map;
+  d.C = C.base; d.ldc = C.ld;
+  d.Cin = accumulate ? C.base : nullptr; d.ldcin = C.ld;
+  d.alpha = alpha;
+  d.tasks = pl.dev + l.off; d.ntasks = l.count; d.bs = bs;
+  return gemm_tasks_launch(h, d);
+}
+
+// recursive panel solve over block-cyclic rows (mirrors trsm_right_lt); consumes the planned GEMMs in order
+int exec_trsm(gpp_handle* h, const Plan& pl, const std::vector<Launch>& gemms, size_t& next, const TrsmRows& rm, const MatRef& Pm, int pc0,
+              const MatRef& Lm, int lr0, int lc0, int nb, int NB) {
+  if (rm.rows <= 0 || nb <= 0) return GPP_OK;
+  if (nb <= 64) return trsm_base_launch(h, Pm.base + pc0, Pm.ld, rm, Lm.base + (long)lr0 * Lm.ld + lc0, Lm.ld, nb);
+  const int hh = (int)round_up((nb + 1) / 2, 64);
+  int rc = exec_trsm(h, pl, gemms, next, rm, Pm, pc0, Lm, lr0, lc0, hh, NB);
+  if (rc) return rc;
+  if (next >= gemms.size()) { h->err = "panel-solve plan exhausted"; return -1; }
+  rc = run_tasks(h, pl, gemms[next++], Pm, Lm, Pm, NB, -1.0, true);
+  if (rc) return rc;
+  return exec_trsm(h, pl, gemms, next, rm, Pm, pc0 + hh, Lm, lr0 + hh, lc0 + hh, nb - hh, NB);
+}
+
+PanelGeom panel_geom(const DistState* d, int n, int NB, int col, int b_lo, int b_hi) {
+  PanelGeom g;
+  g.NB = NB; g.n = n; g.col0 = col * NB; g.w = rows_of(n, NB, col);
+  g.b_lo = b_lo; g.b_hi = b_hi; g.P = d->P;
+  g.cnt_max = (b_hi - b_lo + d->P - 1) / d->P;
+  return g;
+}
+
+// blocks (b, col), b in [b_lo, b_hi), are final on their owners: make them so on every rank (on stream st)
+int gather_panel(gpp_handle* h, DistState* d, double* X, long ld, int n, int NB, int col, int b_lo, int b_hi, cudaStream_t st) {
+  if (d->world <= 1 || b_hi <= b_lo) return GPP_OK;
+  const PanelGeom g = panel_geom(d, n, NB, col, b_lo, b_hi);
+  const int myp = d->rank / d->Q, myq = d->rank % d->Q, cq = col % d->Q;
+  const size_t slot = (size_t)NB * NB;
+  dim3 blk(256);
+  if (myq == cq) {
+    const int first = b_lo + ((myp - b_lo % d->P) + d->P) % d->P;
+    const int cnt = first < b_hi ? (b_hi - first + d->P - 1) / d->P : 0;
+    if (cnt > 0) {
+      panel_copy_kernel<<<dim3(cnt, NB / 64), blk, 0, st>>>(X, ld, d->gbuf, g, 0, myp);
+      h->launches++;
+    }
+  }
+  if (d->Q == 1) {
+    NCCL_TRY(h, ncclAllGather(d->gbuf + (size_t)d->rank * g.cnt_max * slot, d->gbuf, (size_t)g.cnt_max * slot, ncclDouble, d->comm, st));
+  } else {
+    NCCL_TRY(h, ncclGroupStart());
+    for (int pr = 0; pr < d->P; ++pr) {
+      const int first = b_lo + ((pr - b_lo % d->P) + d->P) % d->P;
+      const int cnt = first < b_hi ? (b_hi - first + d->P - 1) / d->P : 0;
+      if (cnt <= 0) continue;
+      double* reg = d->gbuf + (size_t)pr * g.cnt_max * slot;
+      NCCL_TRY(h, ncclBroadcast(reg, reg, (size_t)cnt * slot, ncclDouble, pr * d->Q + cq, d->comm, st));
+    }
+    NCCL_TRY(h, ncclGroupEnd());
+  }
+  panel_copy_kernel<<<dim3(b_hi - b_lo, NB / 64), blk, 0, st>>>(X, ld, d->gbuf, g, 1, myq == cq ? myp : -1);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return GPP_OK;
+}
+
+// diagonal block (j, j) is final on its owner: broadcast it (on stream st)
+int bcast_diag(gpp_handle* h, DistState* d, double* X, long ld, int n, int NB, int j, cudaStream_t st) {
+  if (d->world <= 1) return GPP_OK;
+  const Grid g{d->P, d->Q, d->rank / d->Q, d->rank % d->Q};
+  const int j0 = j * NB, w = rows_of(n, NB, j), root = owner_of(g, j, j);
+  double* blk = X + (long)j0 * ld + j0;
+  if (d->rank == root)
+    CUDA_TRY(h, cudaMemcpy2DAsync(d->dbuf, (size_t)w * 8, blk, ld * 8, (size_t)w * 8, w, cudaMemcpyDeviceToDevice, st));
+  NCCL_TRY(h, ncclBroadcast(d->dbuf, d->dbuf, (size_t)w * w, ncclDouble, root, d->comm, st));
+  if (d->rank != root)
+    CUDA_TRY(h, cudaMemcpy2DAsync(blk, ld * 8, d->dbuf, (size_t)w * 8, (size_t)w * 8, w, cudaMemcpyDeviceToDevice, st));
+  return GPP_OK;
+}
+
+int ensure_staging(gpp_handle* h, DistState* d, int n, int NB) {
+  const int nblk = nblocks_of(n, NB);
+  int rc = dev_reserve(h, &d->gbuf, (size_t)(nblk + d->P) * NB * NB);
+  if (rc) return rc;
+  return dev_reserve(h, &d->dbuf, (size_t)NB * NB);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// distributed right-looking Cholesky of the replicated n x n matrix A (Theta in slot 0, or the GN Hessian)
+// ---------------------------------------------------------------------------------------------------------
+int dist_potrf_matrix(gpp_handle* h, DistState* d, double* A, long ld, int n, const TMap2* map, int phase, bool want_info, int* info) {
+  const int NB = h->NB;
+  const int nblk = nblocks_of(n, NB);
+  const MatRef Am{A, ld, map};
+  const std::vector<Grid> grids = grids_of(d);
+  std::vector<Plan*> plans(grids.size());
+  for (size_t v = 0; v < grids.size(); ++v) {
+    int rc = ensure_plan(h, d, phase, d->nv > 0 ? (int)v : 0, grids[v], n, NB, 0, nullptr, &plans[v]);
+    if (rc) return rc;
+  }
+  int rc = ensure_staging(h, d, n, NB);
+  if (rc) return rc;
+  cudaStream_t S = h->stream;
+  CUDA_TRY(h, cudaMemsetAsync(h->d_info, 0, sizeof(int), S));
+  const Mat Amat{A, ld, map};
+
+  auto panel_factor = [&](const Grid& g, int j) -> int {       // diagonal factorisation on its owner
+    if (owner_of(g, j, j) != g.p * g.Q + g.q) return GPP_OK;
+    return potrf_diag(h, Amat, j * NB, j * NB, rows_of(n, NB, j), j * NB);
+  };
+  auto panel_solve = [&](const Plan& pl, int j) -> int {
+    size_t next = 0;
+    return exec_trsm(h, pl, pl.trsm[j], next, pl.rows[j], Am, j * NB, Am, j * NB, j * NB, rows_of(n, NB, j), NB);
+  };
+
+  if (d->nv > 0) {
+    // virtual ranks, one stream: per step every rank's share in turn (storage is shared, so no exchange)
+    h->cur = S;
+    for (int j = 0; j < nblk && !rc; ++j) {
+      for (size_t v = 0; v < grids.size() && !rc; ++v) rc = panel_factor(grids[v], j);
+      for (size_t v = 0; v < grids.size() && !rc; ++v) rc = panel_solve(*plans[v], j);
+      for (size_t v = 0; v < grids.size() && !rc; ++v) {
+        const Plan& pl = *plans[v];
+        rc = run_tasks(h, pl, pl.la[j], Am, Am, Am, NB, -1.0, true);
+        if (!rc) rc = run_tasks(h, pl, pl.bulkA[j], Am, Am, Am, NB, -1.0, true);
+        if (!rc) rc = run_tasks(h, pl, pl.bulkB[j], Am, Am, Am, NB, -1.0, true);
+      }
+    }
+    if (rc) return rc;
+  } else {
+    const Grid& g = grids[0];
+    const Plan& pl = *plans[0];
+    cudaStream_t Sp = h->sP, Sb = h->sG[0];
+    EventPool ev(h);
+    cudaEvent_t ev0 = ev.get();
+    CUDA_TRY(h, cudaEventRecord(ev0, S));
+    CUDA_TRY(h, cudaStreamWaitEvent(Sp, ev0, 0));
+    CUDA_TRY(h, cudaStreamWaitEvent(Sb, ev0, 0));
+    std::vector<cudaEvent_t> ev_panel(nblk), ev_a(nblk);
+    auto panel = [&](int j) -> int {          // on Sp: factorise, broadcast, solve, gather column j
+      h->cur = Sp;
+      int r = panel_factor(g, j);
+      if (!r) r = bcast_diag(h, d, A, ld, n, NB, j, Sp);
+      if (!r) r = panel_solve(pl, j);
+      if (!r) r = gather_panel(h, d, A, ld, n, NB, j, j + 1, nblk, Sp);
+      return r;
+    };
+    rc = panel(0);
+    for (int j = 0; j < nblk && !rc; ++j) {
+      ev_panel[j] = ev.get();
+      CUDA_TRY(h, cudaEventRecord(ev_panel[j], Sp));
+      if (j + 1 < nblk) {
+        // look-ahead: column j+1 first (it has all updates of the panels < j once bulkA(j-1) is done), then its panel chain
+        if (j >= 1) CUDA_TRY(h, cudaStreamWaitEvent(Sp, ev_a[j - 1], 0));
+        h->cur = Sp;
+        rc = run_tasks(h, pl, pl.la[j], Am, Am, Am, NB, -1.0, true);
+        if (!rc) rc = panel(j + 1);
+        if (rc) break;
+      }
+      CUDA_TRY(h, cudaStreamWaitEvent(Sb, ev_panel[j], 0));
+      h->cur = Sb;
+      rc = run_tasks(h, pl, pl.bulkA[j], Am, Am, Am, NB, -1.0, true);
+      ev_a[j] = ev.get();
+      CUDA_TRY(h, cudaEventRecord(ev_a[j], Sb));
+      if (!rc) rc = run_tasks(h, pl, pl.bulkB[j], Am, Am, Am, NB, -1.0, true);
+    }
+    h->cur = S;
+    if (rc) return rc;
+    cudaEvent_t e1 = ev.get(), e2 = ev.get();
+    CUDA_TRY(h, cudaEventRecord(e1, Sp));
+    CUDA_TRY(h, cudaEventRecord(e2, Sb));
+    CUDA_TRY(h, cudaStreamWaitEvent(S, e1, 0));
+    CUDA_TRY(h, cudaStreamWaitEvent(S, e2, 0));
+  }
+  h->cur = S;
+  if (want_info) {
+    if (d->world > 1) NCCL_TRY(h, ncclAllReduce(h->d_info, h->d_info, 1, ncclInt, ncclMax, d->comm, S));
+    int hinfo = 0;
+    CUDA_TRY(h, cudaMemcpyAsync(&hinfo, h->d_info, sizeof(int), cudaMemcpyDeviceToHost, S));
+    CUDA_TRY(h, cudaStreamSynchronize(S));
+    if (info) *info = hinfo;
+  }
+  return GPP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// U = L^{-T} into the clean replicated buffer d->U
+// ---------------------------------------------------------------------------------------------------------
+int dist_uinv(gpp_handle* h, DistState* d, GramSlot& s) {
+  const int NB = h->NB, n = s.M;
+  const int nblk = nblocks_of(n, NB);
+  const MatRef Um{d->U, s.ld, &d->mapU}, Tm{s.T, s.ld, &s.mapT};
+  const std::vector<Grid> grids = grids_of(d);
+  std::vector<Plan*> plans(grids.size());
+  for (size_t v = 0; v < grids.size(); ++v) {
+    int rc = ensure_plan(h, d, 1, d->nv > 0 ? (int)v : 0, grids[v], n, NB, 0, nullptr, &plans[v]);
+    if (rc) return rc;
+  }
+  int rc = ensure_staging(h, d, n, NB);
+  if (rc) return rc;
+  cudaStream_t S = h->stream;
+  CUDA_TRY(h, cudaMemsetAsync(d->U, 0, sizeof(double) * (size_t)n * s.ld, S));
+
+  auto panel_solve = [&](const Grid& g, const Plan& pl, int i) -> int {     // on h->cur
+    const int i0 = i * NB, nbi = rows_of(n, NB, i);
+    int r = GPP_OK;
+    if (owner_of(g, i, i) == g.p * g.Q + g.q) r = fill_identity_launch(h, d->U + (long)i0 * s.ld + i0, s.ld, nbi, nbi);
+    size_t next = 0;
+    if (!r) r = exec_trsm(h, pl, pl.trsm[i], next, pl.rows[i], Um, i0, Tm, i0, i0, nbi, NB);
+    return r;
+  };
+
+  if (d->nv > 0) {
+    h->cur = S;
+    for (int i = 0; i < nblk && !rc; ++i) {
+      for (size_t v = 0; v < grids.size() && !rc; ++v) rc = panel_solve(grids[v], *plans[v], i);
+      for (size_t v = 0; v < grids.size() && !rc; ++v) {
+        const Plan& pl = *plans[v];
+        rc = run_tasks(h, pl, pl.la[i], Um, Tm, Um, NB, -1.0, true);
+        if (!rc) rc = run_tasks(h, pl, pl.bulkA[i], Um, Tm, Um, NB, -1.0, true);
+        if (!rc) rc = run_tasks(h, pl, pl.bulkB[i], Um, Tm, Um, NB, -1.0, true);
+      }
+    }
+    return rc;
+  }
+  const Grid& g = grids[0];
+  const Plan& pl = *plans[0];
+  cudaStream_t Sp = h->sP, Sb = h->sG[0], Sc = d->sC;
+  EventPool ev(h);
+  cudaEvent_t ev0 = ev.get();
+  CUDA_TRY(h, cudaEventRecord(ev0, S));
+  CUDA_TRY(h, cudaStreamWaitEvent(Sp, ev0, 0));
+  CUDA_TRY(h, cudaStreamWaitEvent(Sb, ev0, 0));
+  CUDA_TRY(h, cudaStreamWaitEvent(Sc, ev0, 0));
+  std::vector<cudaEvent_t> ev_panel(nblk), ev_a(nblk);
+  auto panel = [&](int i) -> int {
+    h->cur = Sp;
+    int r = panel_solve(g, pl, i);
+    if (r) return r;
+    if (d->Q > 1) {
+      // the other process columns need U(b, i) for their updates: gather on the critical path
+      r = gather_panel(h, d, d->U, s.ld, n, NB, i, 0, i + 1, Sp);
+      ev_panel[i] = ev.get();
+      CUDA_TRY(h, cudaEventRecord(ev_panel[i], Sp));
+    } else {
+      // block-row cyclic: a rank only reads its own rows of U; the gather (every rank needs all of U for the next
+      // phase) runs on the communication stream
+      ev_panel[i] = ev.get();
+      CUDA_TRY(h, cudaEventRecord(ev_panel[i], Sp));
+      CUDA_TRY(h, cudaStreamWaitEvent(Sc, ev_panel[i], 0));
+      r = gather_panel(h, d, d->U, s.ld, n, NB, i, 0, i + 1, Sc);
+    }
+    return r;
+  };
+  rc = panel(0);
+  for (int i = 0; i < nblk && !rc; ++i) {
+    if (i + 1 < nblk) {
+      if (i >= 1) CUDA_TRY(h, cudaStreamWaitEvent(Sp, ev_a[i - 1], 0));
+      h->cur = Sp;
+      rc = run_tasks(h, pl, pl.la[i], Um, Tm, Um, NB, -1.0, true);
+      if (rc) break;
+    }
+    // bulk of step i may start as soon as panel i is available (its event was recorded inside panel(i))
+    CUDA_TRY(h, cudaStreamWaitEvent(Sb, ev_panel[i], 0));
+    if (i + 1 < nblk) {
+      rc = panel(i + 1);
+      if (rc) break;
+    }
+    h->cur = Sb;
+    rc = run_tasks(h, pl, pl.bulkA[i], Um, Tm, Um, NB, -1.0, true);
+    ev_a[i] = ev.get();
+    CUDA_TRY(h, cudaEventRecord(ev_a[i], Sb));
+    if (!rc) rc = run_tasks(h, pl, pl.bulkB[i], Um, Tm, Um, NB, -1.0, true);
+  }
+  h->cur = S;
+  if (rc) return rc;
+  cudaEvent_t e1 = ev.get(), e2 = ev.get(), e3 = ev.get();
+  CUDA_TRY(h, cudaEventRecord(e1, Sp));
+  CUDA_TRY(h, cudaEventRecord(e2, Sb));
+  CUDA_TRY(h, cudaEventRecord(e3, Sc));
+  CUDA_TRY(h, cudaStreamWaitEvent(S, e1, 0));
+  CUDA_TRY(h, cudaStreamWaitEvent(S, e2, 0));
+  CUDA_TRY(h, cudaStreamWaitEvent(S, e3, 0));
+  return GPP_OK;
+}
+
+// own sub-blocks of the interior inverse (one launch per virtual rank), on the main stream
+int dist_ablocks(gpp_handle* h, DistState* d, GramSlot& s) {
+  const int NB = h->NB;
+  const std::vector<Grid> grids = grids_of(d);
+  const MatRef Um{d->U, s.ld, &d->mapU};
+  h->cur = h->stream;
+  // virtual ranks share one store: rank v's blocks follow those of ranks < v
+  size_t total_blocks = 0;
+  std::vector<Plan*> plans(grids.size());
+  for (size_t v = 0; v < grids.size(); ++v) {
+    int rc = ensure_plan(h, d, 2, d->nv > 0 ? (int)v : 0, grids[v], s.N, NB, s.M, s.off, &plans[v]);
+    if (rc) return rc;
+    total_blocks += plans[v]->hblocks.size();
+  }
+  int rc = dev_reserve(h, &d->Asub, std::max<size_t>(1, total_blocks) * 4 * NB * NB);
+  if (rc) return rc;
+  d->nbh = NB;
+  size_t base_blocks = 0;
+  for (size_t v = 0; v < grids.size(); ++v) {
+    const Plan& pl = *plans[v];
+    const MatRef Cm{d->Asub + base_blocks * 4 * NB * NB, (long)NB, nullptr};
+    rc = run_tasks(h, pl, pl.all, Um, Um, Cm, NB, 1.0, false);
+    if (rc) return rc;
+    base_blocks += pl.hblocks.size();
+  }
+  return GPP_OK;
 }
 
 }  // namespace
+
+// Hessian blocks of the own (bi, bc) pairs + distributed Cholesky of H; called from gn_step when h->dist_gn
+int dist_gn_hess_potrf(gpp_handle* h) {
+  DistState* d = ds(h);
+  if (!d || !d->inverse_ready) { h->err = "gpp_dist_inverse first"; return -1; }
+  GnState& g = h->gn;
+  const std::vector<Grid> grids = grids_of(d);
+  h->cur = h->stream;
+  size_t base_blocks = 0;
+  for (size_t v = 0; v < grids.size(); ++v) {
+    Plan& pl = plan_slot(d, 2, d->nv > 0 ? (int)v : 0);
+    if (!pl.valid) { h->err = "inverse plan missing"; return -1; }
+    int rc = gn_hess_blocks(h, pl.dev_hblocks, (int)pl.hblocks.size(), d->Asub + base_blocks * 4 * (size_t)d->nbh * d->nbh, d->nbh);
+    if (rc) return rc;
+    base_blocks += pl.hblocks.size();
+  }
+  return dist_potrf_matrix(h, d, g.H, g.ldH, g.n, &g.mapH, 3, false, nullptr);
+}
 
 extern "C" {
 
@@ -71,6 +677,15 @@ int gpp_dist_unique_id(unsigned char* id128) {
   return GPP_OK;
 }
 
+static int dist_common_init(gpp_handle* h, DistState* d) {
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  CUDA_TRY(h, cudaStreamCreateWithPriority(&d->sC, cudaStreamNonBlocking, hi));
+  h->dist = d;
+  h->dist_gn = false;
+  return GPP_OK;
+}
+
 int gpp_dist_init(gpp_handle* h, int rank, int world, const unsigned char* id128) {
   if (h) cudaSetDevice(h->device);
   if (!h || !id128) return -1;
@@ -78,11 +693,41 @@ int gpp_dist_init(gpp_handle* h, int rank, int world, const unsigned char* id128
   if (h->dist) { h->err = "already initialised"; return -3; }
   CUDA_TRY(h, cudaSetDevice(h->device));
   DistState* d = new DistState();
-  d->rank = rank; d->world = world;
+  d->rank = rank; d->world = world; d->P = world; d->Q = 1;
   ncclUniqueId id;
   memcpy(&id, id128, 128);
-  NCCL_TRY(h, ncclCommInitRank(&d->comm, world, id, rank));
-  h->dist = d;
+  ncclResult_t r = ncclCommInitRank(&d->comm, world, id, rank);
+  if (r != ncclSuccess) { h->err = std::string("ncclCommInitRank: ") + ncclGetErrorString(r); delete d; return GPP_CUDA_ERR + 2; }
+  return dist_common_init(h, d);
+}
+
+int gpp_dist_init_virtual(gpp_handle* h, int nranks) {
+  if (h) cudaSetDevice(h->device);
+  if (!h) return -1;
+  if (nranks < 1 || nranks > 64) { h->err = "bad number of virtual ranks"; return -2; }
+  if (h->dist) { h->err = "already initialised"; return -3; }
+  DistState* d = new DistState();
+  d->rank = 0; d->world = 1; d->nv = nranks; d->P = nranks; d->Q = 1;
+  return dist_common_init(h, d);
+}
+
+int gpp_dist_set_grid(gpp_handle* h, int P, int Q) {
+  if (!h || !h->dist) return -1;
+  DistState* d = ds(h);
+  const int n = d->nv > 0 ? d->nv : d->world;
+  if (P < 1 || Q < 1 || P * Q != n) { h->err = "P * Q must equal the number of ranks"; return -2; }
+  d->P = P; d->Q = Q;
+  d->inverse_ready = false;
+  return GPP_OK;
+}
+
+int gpp_dist_info(gpp_handle* h, int* rank, int* world, int* P, int* Q) {
+  if (!h || !h->dist) return -1;
+  DistState* d = ds(h);
+  if (rank) *rank = d->rank;
+  if (world) *world = d->nv > 0 ? d->nv : d->world;
+  if (P) *P = d->P;
+  if (Q) *Q = d->Q;
   return GPP_OK;
 }
 
@@ -91,277 +736,160 @@ int gpp_dist_finalize(gpp_handle* h) {
   if (!h || !h->dist) return -1;
   DistState* d = ds(h);
   cudaStreamSynchronize(h->stream);
+  cudaDeviceSynchronize();
   if (d->comm) ncclCommDestroy(d->comm);
-  if (d->Tloc) cudaFree(d->Tloc);
-  if (d->rowbuf) cudaFree(d->rowbuf);
-  if (d->rowbuf2) cudaFree(d->rowbuf2);
-  if (d->dvec) cudaFree(d->dvec);
+  dev_release(h, &d->U); dev_release(h, &d->Asub); dev_release(h, &d->gbuf); dev_release(h, &d->dbuf); dev_release(h, &d->dvec);
+  for (auto& kv : d->plans) {
+    if (kv.second.dev) cudaFree(kv.second.dev);
+    if (kv.second.dev_hblocks) cudaFree(kv.second.dev_hblocks);
+  }
+  if (d->sC) cudaStreamDestroy(d->sC);
   delete d;
   h->dist = nullptr;
+  h->dist_gn = false;
   return GPP_OK;
 }
 
-// Row-sharded Gram_matrix_assembly (src/Gram_matrice.py:11-187): this rank's block rows of Theta.
+// Sharded Gram_matrix_assembly (src/Gram_matrice.py:11-187): this rank fills the block rows bi with bi mod P == p of the
+// replicated buffer of slot 0 (all column blocks up to the diagonal); no exchange.
 int gpp_dist_gram_assemble(gpp_handle* h, int layout, int kernel, const double* kparams) {
   if (h) cudaSetDevice(h->device);
   if (!h || !h->dist) return -1;
-  if (!h->Xall) { h->err = "points not set"; return -1; }
-  if (layout < 0 || layout > 3 || kernel < 0 || kernel > 1 || !kparams) return -2;
   CUDA_TRY(h, cudaSetDevice(h->device));
+  int rc = gram_slot_prepare(h, 0, layout, kernel, kparams);
+  if (rc) return rc;
   DistState* d = ds(h);
   GramSlot& s = h->slot[0];
-  s.layout_id = layout; s.lay = make_layout(layout);
-  s.N = h->N; s.Nb = (layout == LAY_DARCY_A) ? 0 : h->Nb;
-  int o = 0;
-  for (int p = 0; p < s.lay.nblk; ++p) { s.off[p] = o; o += s.N + (s.lay.with_bdy[p] ? s.Nb : 0); }
-  s.off[s.lay.nblk] = o;
-  s.M = o; s.Mint = s.lay.nblk * s.N;
-  s.kernel_id = kernel;
-  s.kp_b1 = kparams[0]; s.kp_b2 = kparams[1]; s.kp_e1 = kparams[2]; s.kp_e2 = kparams[3];
-  const int NB = h->NB, P = d->world, M = s.M;
-  const int nblk = (M + NB - 1) / NB;
-  int nloc = 0;
-  for (int b = d->rank; b < nblk; b += P) nloc += (M - b * NB < NB) ? (M - b * NB) : NB;
-  const long ld = round_up(M, 16);
-  if (!d->Tloc || d->M != M || d->nloc != nloc) {
-    if (d->Tloc) cudaFree(d->Tloc);
-    if (d->rowbuf) cudaFree(d->rowbuf);
-    if (d->rowbuf2) cudaFree(d->rowbuf2);
-    if (d->dvec) cudaFree(d->dvec);
-    d->M = M; d->nloc = nloc; d->ld = ld;
-    CUDA_TRY(h, cudaMalloc(&d->Tloc, sizeof(double) * (size_t)(nloc > 0 ? nloc : 1) * ld));
-    CUDA_TRY(h, cudaMalloc(&d->rowbuf, sizeof(double) * (size_t)NB * ld));
-    CUDA_TRY(h, cudaMalloc(&d->rowbuf2, sizeof(double) * (size_t)NB * ld));
-    CUDA_TRY(h, cudaMalloc(&d->dvec, sizeof(double) * (size_t)M));
-    if (nloc > 0) {
-      int rc = make_tensor_map(h, &d->mapLoc, d->Tloc, nloc, M, ld);
-      if (rc) return rc;
-    }
-  }
-  d->factored = false;
-  // owned block row b covers global rows [b NB, b NB + nb); split at the row-operator block boundaries
-  for (int b = d->rank; b < nblk; b += P) {
-    const int g0 = b * NB, g1 = (g0 + NB < M) ? g0 + NB : M;
-    const int l0 = local_blk(b, P) * NB;
-    for (int p = 0; p < s.lay.nblk; ++p) {
-      const int lo = g0 > s.off[p] ? g0 : s.off[p];
-      const int hi = g1 < s.off[p + 1] ? g1 : s.off[p + 1];
-      if (hi <= lo) continue;
-      int rc = gram_assemble_rows(h, s, p, lo - s.off[p], hi - lo, d->Tloc + (long)(l0 + lo - g0) * ld, ld);
-      if (rc) return rc;
+  d->inverse_ready = false;
+  h->dist_gn = false;
+  const int NB = h->NB, M = s.M;
+  const int nblk = nblocks_of(M, NB);
+  h->cur = h->stream;
+  for (const Grid& g : grids_of(d)) {
+    if (d->nv > 0 && g.q != 0) continue;           // virtual ranks of one process row hold the same rows
+    for (int b = g.p; b < nblk; b += g.P) {
+      const int g0 = b * NB, g1 = (g0 + NB < M) ? g0 + NB : M;
+      for (int p = 0; p < s.lay.nblk; ++p) {        // split at the row-operator block boundaries
+        const int lo = g0 > s.off[p] ? g0 : s.off[p];
+        const int hi = g1 < s.off[p + 1] ? g1 : s.off[p + 1];
+        if (hi <= lo) continue;
+        rc = gram_assemble_rows(h, s, p, lo - s.off[p], hi - lo, s.T + (long)lo * s.ld, s.ld);
+        if (rc) return rc;
+      }
     }
   }
   return GPP_OK;
 }
 
-int gpp_dist_local_rows(gpp_handle* h, int* nloc, int* M) {
-  if (h) cudaSetDevice(h->device);
-  if (!h || !h->dist) return -1;
-  if (nloc) *nloc = ds(h)->nloc;
-  if (M) *M = ds(h)->M;
-  return GPP_OK;
-}
-
-// diag_out[M]: the full diagonal on every rank (sum all-reduce of the owned parts)
+// diag_out[M]: the full diagonal on every rank (sum all-reduce of the parts held by the owners of the diagonal blocks)
 int gpp_dist_get_diag(gpp_handle* h, double* diag_out) {
   if (h) cudaSetDevice(h->device);
   if (!h || !h->dist || !diag_out) return -1;
   DistState* d = ds(h);
-  const int NB = h->NB, P = d->world, M = d->M;
+  GramSlot& s = h->slot[0];
+  if (!s.T) { h->err = "assemble first"; return -2; }
+  const int NB = h->NB, M = s.M;
+  int rc = dev_reserve(h, &d->dvec, M);
+  if (rc) return rc;
   CUDA_TRY(h, cudaMemsetAsync(d->dvec, 0, sizeof(double) * M, h->stream));
-  for (int b = d->rank; b * NB < M; b += P) {
-    const int g0 = b * NB, nr = (M - g0 < NB) ? (M - g0) : NB;
-    dist_get_diag_kernel<<<(nr + 255) / 256, 256, 0, h->stream>>>(d->Tloc, d->ld, local_blk(b, P) * NB, g0, nr, d->dvec);
-    h->launches++;
-  }
-  NCCL_TRY(h, ncclAllReduce(d->dvec, d->dvec, M, ncclDouble, ncclSum, d->comm, h->stream));
+  for (const Grid& g : grids_of(d))
+    for (int b = 0; b * NB < M; ++b) {
+      if (owner_of(g, b, b) != g.p * g.Q + g.q) continue;
+      const int g0 = b * NB, nr = rows_of(M, NB, b);
+      dist_get_diag_kernel<<<(nr + 255) / 256, 256, 0, h->stream>>>(s.T, s.ld, g0, nr, d->dvec);
+      h->launches++;
+    }
+  if (d->world > 1) NCCL_TRY(h, ncclAllReduce(d->dvec, d->dvec, M, ncclDouble, ncclSum, d->comm, h->stream));
   CUDA_TRY(h, cudaMemcpyAsync(diag_out, d->dvec, sizeof(double) * M, cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   return GPP_OK;
 }
 
+// add a full-length vector to the diagonal entries of the block rows this rank holds
 int gpp_dist_add_diag(gpp_handle* h, const double* add) {
   if (h) cudaSetDevice(h->device);
   if (!h || !h->dist || !add) return -1;
   DistState* d = ds(h);
-  const int NB = h->NB, P = d->world, M = d->M;
+  GramSlot& s = h->slot[0];
+  if (!s.T) { h->err = "assemble first"; return -2; }
+  const int NB = h->NB, M = s.M;
+  int rc = dev_reserve(h, &d->dvec, M);
+  if (rc) return rc;
   CUDA_TRY(h, cudaMemcpyAsync(d->dvec, add, sizeof(double) * M, cudaMemcpyHostToDevice, h->stream));
-  for (int b = d->rank; b * NB < M; b += P) {
-    const int g0 = b * NB, nr = (M - g0 < NB) ? (M - g0) : NB;
-    dist_add_diag_kernel<<<(nr + 255) / 256, 256, 0, h->stream>>>(d->Tloc, d->ld, local_blk(b, P) * NB, g0, nr, d->dvec);
-    h->launches++;
+  for (const Grid& g : grids_of(d)) {
+    if (d->nv > 0 && g.q != 0) continue;
+    for (int b = g.p; b * NB < M; b += g.P) {
+      const int g0 = b * NB, nr = rows_of(M, NB, b);
+      dist_add_diag_kernel<<<(nr + 255) / 256, 256, 0, h->stream>>>(s.T, s.ld, g0, nr, d->dvec);
+      h->launches++;
+    }
   }
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   return GPP_OK;
 }
 
-// Update + solve + own-diagonal update of local rows [lrow, lrow + nrows) in block column j against the received block
-// row (rowbuf holds L[j, 0:(j+1)NB] packed with leading dimension ldrow), on h->cur.
-static int dist_step_rows(gpp_handle* h, DistState* d, int j, int lrow, int nrows, double* rowbuf) {
-  if (nrows <= 0) return GPP_OK;
-  const int NB = h->NB, M = d->M;
-  const int j0 = j * NB;
-  const int nbj = (M - j0 < NB) ? (M - j0) : NB;
-  const long ldrow = j0 + NB;
-  Mat Mloc{d->Tloc, d->ld, &d->mapLoc};
-  TMap2 mapRow;
-  int rc = make_tensor_map(h, &mapRow, rowbuf, nbj, j0 + nbj, ldrow);
-  if (rc) return rc;
-  if (j > 0) {
-    GemmDesc g{};
-    g.mapA = &d->mapLoc; g.mapB = &mapRow;
-    g.a_row0 = lrow; g.b_row0 = 0;
-    g.C = d->Tloc + (long)lrow * d->ld + j0; g.ldc = d->ld; g.Cin = g.C; g.ldcin = d->ld;
-    g.m = nrows; g.n = nbj; g.k0 = 0; g.k1 = j0; g.kb_off = 0; g.alpha = -1.0; g.lower_only = 0;
-    rc = gemm_nt_launch(h, g);
-    if (rc) return rc;
-  }
-  Mat Row{rowbuf, ldrow, &mapRow};
-  rc = trsm_right_lt(h, Mloc, lrow, j0, nrows, Row, 0, j0, nbj);
-  if (rc) return rc;
-  // right-looking update of this rank's own diagonal blocks with the freshly solved column j: keeps every diagonal
-  // block up to date (in column order), so its owner can factorise it the moment its turn comes
-  GemmDesc g{};
-  g.mapA = &d->mapLoc; g.mapB = &d->mapLoc;
-  g.C = d->Tloc; g.ldc = d->ld; g.Cin = d->Tloc; g.ldcin = d->ld;
-  g.k0 = j0; g.k1 = j0 + nbj; g.kb_off = 0; g.alpha = -1.0;
-  g.bd_count = (nrows + NB - 1) / NB; g.bd_world = d->world; g.bd_rank = d->rank; g.bd_lblk0 = lrow / NB; g.bd_nb = NB; g.bd_M = M;
-  return gemm_nt_launch(h, g);
-}
-
-// factorise the (up-to-date) diagonal block of block row j and pack L[j, 0:(j+1)NB] into rowbuf, on h->cur
-static int dist_factor_and_pack(gpp_handle* h, DistState* d, int j, double* rowbuf) {
-  const int NB = h->NB, M = d->M, P = d->world;
-  const int j0 = j * NB;
-  const int nbj = (M - j0 < NB) ? (M - j0) : NB;
-  const long ldrow = j0 + NB;
-  const int lr = local_blk(j, P) * NB;
-  Mat Mloc{d->Tloc, d->ld, &d->mapLoc};
-  int rc = potrf_diag(h, Mloc, lr, j0, nbj, j0);
-  if (rc) return rc;
-  CUDA_TRY(h, cudaMemcpy2DAsync(rowbuf, ldrow * 8, d->Tloc + (long)lr * d->ld, d->ld * 8, (size_t)(j0 + nbj) * 8, nbj,
-                                cudaMemcpyDeviceToDevice, h->cur));
-  return GPP_OK;
-}
-
-// Distributed X.Gram_Cholesky (src/PDEs.py:75-80).  *info as in gpp_potrf, identical on every rank.
-//
-// Look-ahead: the owner of block row j+1 treats that block row first (high-priority stream sP): update + solve in
-// column j, factorise its diagonal block, pack, broadcast -- while every rank is still busy with the bulk of
-// column j on the main stream.  Two row buffers alternate; events order bulk(j) after bcast(j) and bcast(j+2) after
-// bulk(j).  NCCL calls are issued in the same order (j = 0, 1, ...) on the side stream of every rank.
+// Distributed X.Gram_Cholesky (src/PDEs.py:75-80).  *info as in gpp_potrf, identical on every rank.  Afterwards every
+// rank holds the full factor: gpp_gn_loss, gpp_solve_vec, gpp_predict and gpp_gram_download(.., 1) work unchanged.
 int gpp_dist_potrf(gpp_handle* h, int* info) {
   if (h) cudaSetDevice(h->device);
   if (!h || !h->dist) return -1;
   DistState* d = ds(h);
-  if (!d->Tloc) { h->err = "assemble first"; return -2; }
-  if (d->factored) { h->err = "already factored"; return -3; }
+  GramSlot& s = h->slot[0];
+  if (!s.T) { h->err = "assemble first"; return -2; }
+  if (s.factored) { h->err = "already factored"; return -3; }
   CUDA_TRY(h, cudaSetDevice(h->device));
-  const int NB = h->NB, P = d->world, M = d->M, rank = d->rank;
-  const int nblk = (M + NB - 1) / NB;
-  cudaStream_t S = h->stream, Sp = h->sP;
-  double* rb[2] = {d->rowbuf, d->rowbuf2};
-  CUDA_TRY(h, cudaMemsetAsync(h->d_info, 0, sizeof(int), S));
-  size_t used = 0;
-  auto new_event = [&]() {
-    if (used == h->evpool.size()) {
-      cudaEvent_t e;
-      cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
-      h->evpool.push_back(e);
-    }
-    return h->evpool[used++];
-  };
-  constexpr int NREG = 3;
-  auto clampi = [&](long v) { return (int)(v > d->nloc ? d->nloc : v); };
-  const int bound[NREG + 1] = {0, clampi(round_up(d->nloc / 2, NB)), clampi(round_up((3L * d->nloc) / 4, NB)), d->nloc};
-  std::vector<cudaEvent_t> ev_bc(nblk), ev_bulk(NREG * nblk);
-  cudaEvent_t ev0 = new_event();
-  CUDA_TRY(h, cudaEventRecord(ev0, S));
-  CUDA_TRY(h, cudaStreamWaitEvent(Sp, ev0, 0));
-  for (int k = 0; k < 2; ++k) CUDA_TRY(h, cudaStreamWaitEvent(h->sG[k], ev0, 0));
-  auto bcast = [&](int j) -> int {     // on Sp
-    const int j0 = j * NB;
-    const int nbj = (M - j0 < NB) ? (M - j0) : NB;
-    if (P > 1) NCCL_TRY(h, ncclBroadcast(rb[j & 1], rb[j & 1], (size_t)nbj * (j0 + NB), ncclDouble, owner_of(j, P), d->comm, Sp));
-    ev_bc[j] = new_event();
-    CUDA_TRY(h, cudaEventRecord(ev_bc[j], Sp));
-    return GPP_OK;
-  };
-  int rc = GPP_OK;
-  // prologue: block row 0
-  h->cur = Sp;
-  if (rank == owner_of(0, P)) rc = dist_factor_and_pack(h, d, 0, rb[0]);
-  if (!rc) rc = bcast(0);
-  for (int j = 0; j < nblk && !rc; ++j) {
-    const int lstart = owned_upto(j, rank, P) * NB;        // first local row below block row j
-    int bulk_start = lstart;
-    if (j + 1 < nblk) {
-      // rb[(j+1)&1] was last read by bulk(j-1); block row j+1's earlier columns were written by bulk(<= j-1)
-      if (j >= 1) {
-        for (int k = 0; k < NREG; ++k) CUDA_TRY(h, cudaStreamWaitEvent(Sp, ev_bulk[NREG * (j - 1) + k], 0));
-      }
-      if (rank == owner_of(j + 1, P)) {
-        h->cur = Sp;
-        const int nb1 = (M - (j + 1) * NB < NB) ? (M - (j + 1) * NB) : NB;
-        rc = dist_step_rows(h, d, j, lstart, nb1, rb[j & 1]);   // block row j+1 is this rank's first row block below j
-        if (!rc) rc = dist_factor_and_pack(h, d, j + 1, rb[(j + 1) & 1]);
-        if (rc) break;
-        bulk_start = lstart + NB;
-      }
-      rc = bcast(j + 1);
-      if (rc) break;
-    }
-    // bulk of column j: the remaining rows, cut at fixed local-row boundaries into regions that stay on the same
-    // stream for the whole factorisation.  A row only depends on its own history and on the received block row, so
-    // region A may start column j+1 while region B still finishes column j: the second stream fills the SMs the last
-    // wave of the other one leaves idle.
-    for (int k = 0; k < NREG && !rc; ++k) {
-      const int lo = bulk_start > bound[k] ? bulk_start : bound[k];
-      const int hi = bound[k + 1];
-      cudaStream_t sg = h->sG[k & 1];
-      CUDA_TRY(h, cudaStreamWaitEvent(sg, ev_bc[j], 0));
-      h->cur = sg;
-      if (hi > lo) rc = dist_step_rows(h, d, j, lo, hi - lo, rb[j & 1]);
-      ev_bulk[NREG * j + k] = new_event();
-      CUDA_TRY(h, cudaEventRecord(ev_bulk[NREG * j + k], sg));
-    }
-  }
-  h->cur = S;
+  int rc = dist_potrf_matrix(h, d, s.T, s.ld, s.M, &s.mapT, 0, true, info);
   if (rc) return rc;
-  {
-    cudaEvent_t e = new_event();
-    CUDA_TRY(h, cudaEventRecord(e, Sp));
-    CUDA_TRY(h, cudaStreamWaitEvent(S, e, 0));
-    for (int k = 0; k < 2; ++k) {
-      cudaEvent_t eg = new_event();
-      CUDA_TRY(h, cudaEventRecord(eg, h->sG[k]));
-      CUDA_TRY(h, cudaStreamWaitEvent(S, eg, 0));
-    }
-  }
-  if (P > 1) NCCL_TRY(h, ncclAllReduce(h->d_info, h->d_info, 1, ncclInt, ncclMax, d->comm, S));
-  int hinfo = 0;
-  CUDA_TRY(h, cudaMemcpyAsync(&hinfo, h->d_info, sizeof(int), cudaMemcpyDeviceToHost, S));
-  CUDA_TRY(h, cudaStreamSynchronize(S));
-  if (info) *info = hinfo;
-  d->factored = true;
+  s.factored = true;
+  s.inverted = false;
   return GPP_OK;
 }
 
-// out: nloc x M dense rows of this rank (lower triangle of Theta / L; entries above the diagonal are zeroed)
-int gpp_dist_download_local(gpp_handle* h, double* out) {
+// Distributed counterpart of gpp_inverse for the elliptic layout: U = L^{-T} (sharded, then replicated) and the
+// sub-blocks of the interior inverse that this rank's Hessian blocks need.  Enables gpp_dist_gn_step.
+int gpp_dist_inverse(gpp_handle* h) {
   if (h) cudaSetDevice(h->device);
-  if (!h || !h->dist || !out) return -1;
+  if (!h || !h->dist) return -1;
   DistState* d = ds(h);
-  const int NB = h->NB, P = d->world, M = d->M;
-  CUDA_TRY(h, cudaMemcpy2DAsync(out, (size_t)M * 8, d->Tloc, d->ld * 8, (size_t)M * 8, d->nloc, cudaMemcpyDeviceToHost, h->stream));
-  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-  long lr = 0;
-  for (int b = d->rank; b * NB < M; b += P) {
-    const int g0 = b * NB, nr = (M - g0 < NB) ? (M - g0) : NB;
-    for (int i = 0; i < nr; ++i, ++lr)
-      for (int c = g0 + i + 1; c < M; ++c) out[lr * M + c] = 0.0;
+  GramSlot& s = h->slot[0];
+  if (!s.factored) { h->err = "gpp_dist_potrf first"; return -2; }
+  if (s.layout_id != LAY_ELLIPTIC) { h->err = "the sharded GN path supports the elliptic layout only"; return -3; }
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  int rc = dev_reserve(h, &d->U, (size_t)s.M * s.ld);
+  if (rc) return rc;
+  rc = make_tensor_map(h, &d->mapU, d->U, s.M, s.M, s.ld);
+  if (rc) return rc;
+  static const bool trace = getenv("GPP_TRACE") != nullptr;
+  if (trace) cudaEventRecord(h->ev[2], h->stream);
+  rc = dist_uinv(h, d, s);
+  if (rc) return rc;
+  if (trace) cudaEventRecord(h->ev[3], h->stream);
+  rc = dist_ablocks(h, d, s);
+  if (rc) return rc;
+  if (trace) {
+    cudaEventRecord(h->ev[4], h->stream);
+    cudaEventSynchronize(h->ev[4]);
+    float t1 = 0, t2 = 0;
+    cudaEventElapsedTime(&t1, h->ev[2], h->ev[3]);
+    cudaEventElapsedTime(&t2, h->ev[3], h->ev[4]);
+    fprintf(stderr, "[gpp trace] dist inverse (rank %d): U = L^-T %.2f ms | A blocks %.2f ms\n", d->rank, t1, t2);
   }
+  d->inverse_ready = true;
+  h->dist_gn = true;
   return GPP_OK;
+}
+
+// one iteration of GN_method's loop body (src/PDEs.py:117-120) with the sharded Hessian assembly and the distributed
+// Cholesky of H; every rank ends with the same z and returns the same loss
+int gpp_dist_gn_step(gpp_handle* h, double step, double* loss) {
+  if (h) cudaSetDevice(h->device);
+  if (!h || !h->dist) return -1;
+  if (!h->gn.ready) { h->err = "gpp_gn_setup first"; return -1; }
+  if (h->gn.pde != PDE_ELLIPTIC) { h->err = "the sharded GN path supports Nonlinear_elliptic only"; return -2; }
+  if (!ds(h)->inverse_ready || !h->dist_gn) { h->err = "gpp_dist_inverse first"; return -3; }
+  if (!loss) return -4;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  return gn_step(h, step, loss);
 }
 
 }  // extern "C"

@@ -46,6 +46,9 @@ struct GemmParams {
   // block-diagonal batch mode (multi-GPU Cholesky): tile t -> local block row bd_lblk0 + t / ntri, lower tile t % ntri of
   // the NB x NB diagonal block of that block row; global column of the block = ((lblk * bd_world) + bd_rank) * bd_nb
   int bd_mode, bd_world, bd_rank, bd_lblk0, bd_nb, bd_M;
+  // task-list mode (multi-GPU path): blockIdx.x / (task_tps^2) indexes tasks[]; see GemmTask in gpp_internal.cuh
+  const GemmTask* tasks;
+  int task_tps;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -136,12 +139,26 @@ gemm_nt_dmma_kernel(const __grid_constant__ GemmParams p) {
     if (row_base >= m_lim || col_base >= n_lim) return;
   }
 
-  int k_lo = p.k0;
+  int k_lo = p.k0, k_hi = p.k1, kb_off = p.kb_off;
+  if (p.tasks) {
+    const int per = p.task_tps * p.task_tps;
+    const int4* tp = reinterpret_cast<const int4*>(p.tasks + blockIdx.x / per);
+    const int4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);   // {a_row, b_row, c_row, c_col} {m, n, k0, k1} {kb_off, tri, -, -}
+    const int tile = blockIdx.x % per;
+    const int ti = tile / p.task_tps, tj = tile % p.task_tps;
+    row_base = ti * BM; col_base = tj * BN;
+    if (row_base >= t1.x || col_base >= t1.y || (t2.y && tj > ti)) return;     // uniform over the CTA, before any barrier
+    a_row = t0.x + row_base; b_row = t0.y + col_base;
+    Cp = p.C + (long)t0.z * p.ldc + t0.w;
+    Cinp = p.Cin ? p.Cin + (long)t0.z * p.ldcin + t0.w : nullptr;
+    m_lim = t1.x; n_lim = t1.y;
+    k_lo = t1.z; k_hi = t1.w; kb_off = t2.x;
+  }
   if (p.ktri) {
     int kb = (a_row / p.diag_nb) * p.diag_nb;
     if (kb > k_lo) k_lo = kb;
   }
-  const int nchunks = (p.k1 > k_lo) ? (p.k1 - k_lo + BK - 1) / BK : 0;
+  const int nchunks = (k_hi > k_lo) ? (k_hi - k_lo + BK - 1) / BK : 0;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -167,7 +184,7 @@ gemm_nt_dmma_kernel(const __grid_constant__ GemmParams p) {
         if (p.has_adiag && kblk == a_dblk) tma_load_2d(sa, &p.mapAdiag, &full[s], k - kblk * p.diag_nb, a_row);
         else tma_load_2d(sa, &p.mapA, &full[s], k, a_row);
         if (p.has_bdiag && kblk == b_dblk) tma_load_2d(sb, &p.mapBdiag, &full[s], k - kblk * p.diag_nb, b_row);
-        else tma_load_2d(sb, &p.mapB, &full[s], k + p.kb_off, b_row);
+        else tma_load_2d(sb, &p.mapB, &full[s], k + kb_off, b_row);
       }
     }
     return;
@@ -331,6 +348,7 @@ int gemm_nt_launch(gpp_handle* h, const GemmDesc& d) {
   p.diag_nb = d.diag_nb > 0 ? d.diag_nb : (1 << 30);
   p.alpha = d.alpha; p.lower_only = d.lower_only;
   p.bd_mode = d.bd_count > 0; p.bd_world = d.bd_world; p.bd_rank = d.bd_rank; p.bd_lblk0 = d.bd_lblk0; p.bd_nb = d.bd_nb; p.bd_M = d.bd_M;
+  p.tasks = nullptr; p.task_tps = 0;
   // tile choice: 64 x 64 when the 128-tiling would occupy less than half of the SMs
   long t128;
   if (p.bd_mode) { const int nt = d.bd_nb / 128; t128 = (long)d.bd_count * (nt * (nt + 1) / 2); }
@@ -338,4 +356,40 @@ int gemm_nt_launch(gpp_handle* h, const GemmDesc& d) {
   const int force = h->force_tile;
   const bool small = force ? (force == 64) : (t128 < 74);
   return small ? launch_tile<64>(h, d, p) : launch_tile<128>(h, d, p);
+}
+
+namespace {
+template <int TILE>
+int launch_tasks(gpp_handle* h, const GemmTaskDesc& d, GemmParams& p) {
+  p.mapA = TILE == 128 ? d.mapA->m128 : d.mapA->m64;
+  p.mapB = TILE == 128 ? d.mapB->m128 : d.mapB->m64;
+  p.mapAdiag = p.mapA; p.mapBdiag = p.mapB;
+  static bool attr_set[64] = {false};
+  if (h->device >= 64 || !attr_set[h->device]) {
+    CUDA_TRY(h, cudaFuncSetAttribute(gemm_nt_dmma_kernel<TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<TILE>::SMEM_BYTES));
+    if (h->device < 64) attr_set[h->device] = true;
+  }
+  p.task_tps = d.bs / TILE;
+  const long ntiles = (long)d.ntasks * p.task_tps * p.task_tps;
+  gemm_nt_dmma_kernel<TILE><<<(unsigned)ntiles, Cfg<TILE>::THREADS, Cfg<TILE>::SMEM_BYTES, h->cur>>>(p);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return GPP_OK;
+}
+}  // namespace
+
+int gemm_tasks_launch(gpp_handle* h, const GemmTaskDesc& d) {
+  if (d.ntasks <= 0) return GPP_OK;
+  if (d.bs <= 0 || d.bs % 128) { h->err = "task block size must be a multiple of 128"; return -1; }
+  GemmParams p{};
+  p.has_adiag = p.has_bdiag = 0;
+  p.C = d.C; p.ldc = d.ldc; p.Cin = d.Cin; p.ldcin = d.ldcin;
+  p.diag_nb = 1 << 30;
+  p.alpha = d.alpha;
+  p.tasks = d.tasks;
+  p.tiles_m = p.tiles_n = 1;     // unused in task mode (kept non-zero: the generic tile decode still runs)
+  const long t128 = (long)d.ntasks * (d.bs / 128) * (d.bs / 128);
+  const int force = h->force_tile;
+  const bool small = force ? (force == 64) : (t128 < 74);
+  return small ? launch_tasks<64>(h, d, p) : launch_tasks<128>(h, d, p);
 }

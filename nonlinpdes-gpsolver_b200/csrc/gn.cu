@@ -226,6 +226,38 @@ hess_kernel(const __grid_constant__ HParams a) {
   }
 }
 
+// multi-GPU (elliptic): one launch covers the Hessian blocks (bi, bc) this rank owns.  A sub-blocks of block e sit at rows
+// (4 e + 2 p + p') * nbh of a compact store with leading dimension nbh.  Same term order as hess_kernel:
+// H_ij = 2 ((c_i A00) c_j + (c_i A01) 1 + (1 A10) c_j + (1 A11) 1)                       src/PDEs.py:94-102
+__global__ void __launch_bounds__(256)
+hess_blocks_kernel(const int4* __restrict__ blocks, const double* __restrict__ Asub, int nbh, int N,
+                   const double* __restrict__ c0, const double* __restrict__ c1, double* __restrict__ H, long ldH) {
+  const int4 b = blocks[blockIdx.z];
+  const int j = blockIdx.x * 64 + (threadIdx.x & 63);
+  const int ibase = blockIdx.y * 16 + (threadIdx.x >> 6) * 4;
+  const int gj = b.y * nbh + j;
+  if (j >= nbh || gj >= N) return;
+  const double* A00 = Asub + (long)(b.z * 4 + 0) * nbh * nbh;
+  const double* A01 = Asub + (long)(b.z * 4 + 1) * nbh * nbh;
+  const double* A10 = Asub + (long)(b.z * 4 + 2) * nbh * nbh;
+  const double* A11 = Asub + (long)(b.z * 4 + 3) * nbh * nbh;
+  const double cj0 = c0[gj], cj1 = c1[gj];
+#pragma unroll
+  for (int ii = 0; ii < 4; ++ii) {
+    const int i = ibase + ii;
+    const int gi = b.x * nbh + i;
+    if (i >= nbh || gi >= N) break;
+    const double ci0 = c0[gi], ci1 = c1[gi];
+    const long e = (long)i * nbh + j;
+    double acc = 0.0;
+    acc += (ci0 * A00[e]) * cj0;
+    acc += (ci0 * A01[e]) * cj1;
+    acc += (ci1 * A10[e]) * cj0;
+    acc += (ci1 * A11[e]) * cj1;
+    H[(long)gi * ldH + gj] = 2.0 * acc;
+  }
+}
+
 struct GParams {
   int N, nz, nslots;
   int nblk[GPP_MAX_SLOTS];
@@ -338,6 +370,50 @@ int gn_loss(gpp_handle* h, const double* d_z, double* loss_host) {
   return GPP_OK;
 }
 
+int gn_hess_blocks(gpp_handle* h, const int4* d_blocks, int nblocks, const double* Asub, int nbh) {
+  GnState& g = h->gn;
+  if (g.pde != PDE_ELLIPTIC) { h->err = "sharded Hessian assembly: elliptic only"; return -1; }
+  if (nblocks <= 0) return GPP_OK;
+  const int N = h->N;
+  const double* c0 = g.coef + ((long)((0 * GPP_MAX_BLOCKS + 0) * GPP_MAX_ZBLOCKS + 0)) * N;
+  const double* c1 = g.coef + ((long)((0 * GPP_MAX_BLOCKS + 1) * GPP_MAX_ZBLOCKS + 0)) * N;
+  for (int b0 = 0; b0 < nblocks; b0 += 32768) {
+    const int nb = (nblocks - b0 < 32768) ? (nblocks - b0) : 32768;
+    dim3 grid((nbh + 63) / 64, (nbh + 15) / 16, nb);
+    hess_blocks_kernel<<<grid, 256, 0, h->cur>>>(d_blocks + b0, Asub, nbh, N, c0, c1, g.H, g.ldH);
+    h->launches++;
+  }
+  CUDA_TRY(h, cudaGetLastError());
+  return GPP_OK;
+}
+
+// t = L^{-T} s and g = grad loss(z); requires F, s and coef of g.z to be current.
+int gn_grad(gpp_handle* h) {
+  GnState& g = h->gn;
+  const int ns = nslots_of(g);
+  const int N = h->N;
+  set_kind(g);
+  int rc;
+  for (int s = 0; s < ns; ++s) {
+    GramSlot& sl = h->slot[s];
+    CUDA_TRY(h, cudaMemcpyAsync(g.t[s], g.s[s], sizeof(double) * sl.M, cudaMemcpyDeviceToDevice, h->stream));
+    rc = trsv_lower(h, sl.T, sl.ld, sl.M, g.t[s], true);
+    if (rc) return rc;
+  }
+  GParams a{};
+  a.N = N; a.nz = g.nz; a.nslots = ns;
+  for (int s = 0; s < ns; ++s) { a.nblk[s] = h->slot[s].lay.nblk; a.t[s] = g.t[s]; }
+  memcpy(a.kind, g.coef_kind, sizeof(a.kind));
+  a.coef = g.coef; a.g = g.g;
+  a.data_block = (g.pde == PDE_DARCY) ? 3 : -1; a.ndata = g.N_data;
+  a.data_scale = (g.pde == PDE_DARCY) ? 2.0 / (g.noise * g.noise) : 0.0;
+  a.z = g.z; a.data = g.data_u;
+  grad_kernel<<<(N + 255) / 256, 256, 0, h->stream>>>(a);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return GPP_OK;
+}
+
 // g = grad loss(z) and H = Hessian_GN(z, z) at g.z; requires F, s and coef of g.z to be current.
 int gn_grad_hess(gpp_handle* h) {
   GnState& g = h->gn;
@@ -415,12 +491,21 @@ int gn_step(gpp_handle* h, double step, double* loss_host) {
   }
   mark(0);
   mark(1);
-  rc = gn_grad_hess(h);
-  if (rc) return rc;
-  mark(2);
-  // delta = H^{-1} g via Cholesky (H is SPD: 2 S^T S + data term)
-  rc = potrf_lower(h, g.H, g.ldH, g.n, &g.mapH);
-  if (rc) return rc;
+  if (h->dist_gn) {
+    // sharded: gradient replicated, Hessian blocks by their owners, distributed Cholesky of H (dist.cu)
+    rc = gn_grad(h);
+    if (rc) return rc;
+    mark(2);
+    rc = dist_gn_hess_potrf(h);
+    if (rc) return rc;
+  } else {
+    rc = gn_grad_hess(h);
+    if (rc) return rc;
+    mark(2);
+    // delta = H^{-1} g via Cholesky (H is SPD: 2 S^T S + data term)
+    rc = potrf_lower(h, g.H, g.ldH, g.n, &g.mapH);
+    if (rc) return rc;
+  }
   mark(3);
   rc = trsv_lower(h, g.H, g.ldH, g.n, g.g, false);
   if (rc) return rc;

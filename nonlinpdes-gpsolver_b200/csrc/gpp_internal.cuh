@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <vector>
@@ -116,6 +117,7 @@ struct gpp_handle {
   long launches = 0;
   // distributed (dist.cu)
   void* dist = nullptr;
+  bool dist_gn = false;               // GN steps use the sharded Hessian assembly + distributed Cholesky of H
   // capacity (doubles) of every device buffer obtained through dev_reserve, keyed by the address of its pointer:
   // buffers are grown, never shrunk, so repeated solves on one handle do not touch the allocator
   std::map<double**, size_t> caps;
@@ -172,6 +174,28 @@ struct GemmDesc {
   int bd_count, bd_world, bd_rank, bd_lblk0, bd_nb, bd_M;
 };
 int gemm_nt_launch(gpp_handle* h, const GemmDesc& d);
+
+// Task-list mode of the same kernel (multi-GPU path): one task = one output block of up to bs x bs elements, processed
+// by (bs / TILE)^2 CTAs.  C[c_row + i, c_col + j] (+)= alpha * sum_{k in [k0, k1)} A[a_row + i, k] * B[b_row + j, k + kb_off]
+// for i < m, j < n; tri != 0: the block lies on the diagonal of a symmetric matrix, tiles strictly above it are skipped.
+struct GemmTask {
+  int a_row, b_row;
+  int c_row, c_col;
+  int m, n;
+  int k0, k1;
+  int kb_off, tri;
+  int pad0, pad1;
+};
+static_assert(sizeof(GemmTask) == 48, "GemmTask is read as three 16-byte words");
+struct GemmTaskDesc {
+  const TMap2* mapA; const TMap2* mapB;
+  double* C; long ldc;              // matrix origin (tasks carry the block position)
+  const double* Cin; long ldcin;    // optional addend origin (may alias C)
+  double alpha;
+  const GemmTask* tasks;            // device pointer
+  int ntasks, bs;                   // bs: task block size, a multiple of 128
+};
+int gemm_tasks_launch(gpp_handle* h, const GemmTaskDesc& d);
 int make_tensor_map(gpp_handle* h, TMap2* map, const double* base, long rows, long cols, long ld);
 
 // ---- chol.cu ---------------------------------------------------------------
@@ -180,6 +204,15 @@ struct Mat {
   long ld;
   const TMap2* map;
 };
+// rows of a panel solve: contiguous (stride_blk == 0) or block-cyclic: logical row block b of `nb` rows sits at
+// physical rows (first_blk + b * stride_blk) * nb
+struct TrsmRows {
+  int rows;
+  int first_blk, stride_blk, nb;
+};
+// 64-wide base case of the panel solve X L^T = P (in place), L = nbl x nbl lower block; P points at column 0 of the panel
+int trsm_base_launch(gpp_handle* h, double* P, long ldp, const TrsmRows& rm, const double* L, long ldl, int nbl);
+int fill_identity_launch(gpp_handle* h, double* A, long ld, int rows, int cols);
 // X * L^T = P in place; P = rows x nb block of P at (pr0, pc0); L = nb x nb lower block of L at (lr0, lc0)
 int trsm_right_lt(gpp_handle* h, const Mat& P, int pr0, int pc0, int rows, const Mat& L, int lr0, int lc0, int nb);
 // Cholesky of the nb x nb block at (r0, c0) of A (recursive, 64-wide base), gidx0 = global pivot offset
@@ -193,6 +226,8 @@ int inverse_interior(gpp_handle* h, GramSlot& s);
 // y = L^{-1} b (forward) / y = L^{-T} b (backward), vectors, in place in x
 int trsv_lower(gpp_handle* h, const double* L, long ld, int n, double* x, bool transposed);
 
+// ---- capi.cu: size / layout bookkeeping, buffer and tensor map of a Gram slot (no assembly)
+int gram_slot_prepare(gpp_handle* h, int slot, int layout, int kernel, const double* kparams);
 // ---- gram.cu ---------------------------------------------------------------
 int gram_assemble(gpp_handle* h, GramSlot& s);
 int gram_predict(gpp_handle* h, GramSlot& s, const double* d_xtest, int ntest, const double* d_w, double* d_out);
@@ -203,5 +238,10 @@ int gn_eval_F(gpp_handle* h, const double* d_z, bool with_coef);
 int gn_loss(gpp_handle* h, const double* d_z, double* loss_host);
 int gn_step(gpp_handle* h, double step, double* loss_host);
 int gn_grad_hess(gpp_handle* h);
+int gn_grad(gpp_handle* h);           // t = L^{-T} s and the gradient
+// multi-GPU (elliptic): H blocks listed in d_blocks (int4: bi, bc, index of the 2 x 2 group of A sub-blocks, unused) from
+// the compact sub-block store Asub (blocks of nbh x nbh, leading dimension nbh, order (p, p') = 00, 01, 10, 11)
+int dist_gn_hess_potrf(gpp_handle* h);   // dist.cu
+int gn_hess_blocks(gpp_handle* h, const int4* d_blocks, int nblocks, const double* Asub, int nbh);
 int gram_kernel_eval(gpp_handle* h, int kernel, const double* kparams, int opx, int opy, const double* d_in, long n,
                      double* d_out);

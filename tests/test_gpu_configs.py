@@ -87,7 +87,8 @@ def test_C1_elliptic_through_facade(solver_GP):
     assert rel(s.pts_L2_err, rl2) <= tol and rel(s.pts_max_err, rmax) <= tol
     assert rel(s.test_L2_err, tl2) <= tol and rel(s.test_max_err, tmax) <= tol
     assert s.pts_L2_err < 1e-6                            # and the solve itself is accurate (2e-7 in round 1)
-    np.testing.assert_allclose(s.eqn.loss_hist[:2], ref.loss_hist[:2], rtol=1e-6)
+    # F^T Theta^{-1} F at the random initial guess is dominated by the smallest eigen-directions of Theta: same band
+    np.testing.assert_allclose(s.eqn.loss_hist, ref.loss_hist, rtol=tol)
 
 
 def test_C2_burgers_through_facade(solver_GP):
