@@ -20,11 +20,14 @@ def _check(line):
     cb = j["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and "sample" in cb and cb["value"] == j["value"] and j["value"] > 0
     assert "workload" in j["config"]
+    assert cb["extrapolated"] is True and j["same_config"] is False          # the workload size itself is never run on the CPU
+    big = cb["measured_at_largest_size"]
+    assert big["N_domain"] == 300 and big["steps_per_s"] > 0
 
 
 def test_reference_arm_single_process():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                          "--cpu_sample_N", "200", "--N_domain", "2000"], capture_output=True, text=True, timeout=600)
+                          "--cpu_sample_N", "200", "--cpu_big_N", "300", "--N_domain", "2000"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-1500:]
     lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
@@ -34,7 +37,7 @@ def test_reference_arm_single_process():
 def test_reference_arm_under_torchrun_only_rank0_prints():
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                           "--master-port", "29631", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
-                          "--warmup", "0", "--cpu_sample_N", "200", "--N_domain", "2000"], capture_output=True, text=True, timeout=600)
+                          "--warmup", "0", "--cpu_sample_N", "200", "--cpu_big_N", "300", "--N_domain", "2000"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-1500:]
     lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
