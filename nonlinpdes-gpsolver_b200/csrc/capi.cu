@@ -135,6 +135,7 @@ int gpp_destroy(gpp_handle* h) {
   for (int s = 0; s < GPP_MAX_SLOTS; ++s) { dev_free(g.F[s]); dev_free(g.s[s]); dev_free(g.t[s]); }
   if (h->work) cudaFree(h->work);
   if (h->d_info) cudaFree(h->d_info);
+  if (h->d_trsv_flag) cudaFree(h->d_trsv_flag);
   for (auto& e : h->ev) cudaEventDestroy(e);
   for (auto& e : h->evpool) cudaEventDestroy(e);
   if (h->sP) cudaStreamDestroy(h->sP);

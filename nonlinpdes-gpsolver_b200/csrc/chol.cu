@@ -144,72 +144,155 @@ __global__ void symmetrize_kernel(double* __restrict__ A, long ld, int n) {
 }
 
 // ---------------------------------------------------------------------------
-// vector triangular solves, 64-wide blocks
+// Vector triangular solves  L x = b  /  L^T x = b  (in place in x): ONE persistent kernel.
+//
+// 64-row blocks; CTA c owns blocks c, c + G, c + 2G, ... (G = resident CTAs, so every CTA is on the device and the
+// spin-waits below cannot deadlock).  For its block rb a CTA streams the 64 x 64 blocks L[rb, jb], jb < rb (forward; for
+// the transposed solve L[jb, rb], jb > rb) against the finished parts of x, each as soon as the global counter `done`
+// says x[jb] is final; then it solves the diagonal block (one warp, 64 shuffle steps, reciprocal diagonal prepared off
+// the critical path), publishes x[rb] and advances the counter (release / acquire at GPU scope).
+// The L blocks are issued before the wait, so the only serial part per block is: counter round trip, one 64 x 64
+// product, the cross-warp reduction and the diagonal solve.  Replaces two launches per 64 rows (jnp.linalg.solve(L, vec)
+// in the reference: src/PDEs.py:86, :205).
 // ---------------------------------------------------------------------------
-// solve the diagonal block in place: forward (L x = b) or backward (L^T x = b)
-__global__ void __launch_bounds__(256)
-trsv_diag_kernel(const double* __restrict__ L, long ld, int nb, double* __restrict__ x, int transposed) {
-  __shared__ double s[BASE * LDS_PAD];
-  __shared__ double xs[BASE];
-  const int tid = threadIdx.x;
-  {
-    const int c = tid & 63;
-    for (int r = tid >> 6; r < nb; r += 4)     // 4 rows per pass, coalesced
-      if (c <= r) s[r * LDS_PAD + c] = L[(long)r * ld + c];
-  }
-  if (tid < nb) xs[tid] = x[tid];
-  __syncthreads();
-  if (tid >= BASE) return;
-  // two warps; column-oriented substitution, x_j published through shared memory
-  if (!transposed) {
-    for (int j = 0; j < nb; ++j) {
-      if (tid == j) xs[j] = xs[j] / s[j * LDS_PAD + j];
-      asm volatile("bar.sync 1, 64;");
-      if (tid > j && tid < nb) xs[tid] = fma(-s[tid * LDS_PAD + j], xs[j], xs[tid]);
-      asm volatile("bar.sync 1, 64;");
-    }
-  } else {
-    for (int j = nb - 1; j >= 0; --j) {
-      if (tid == j) xs[j] = xs[j] / s[j * LDS_PAD + j];
-      asm volatile("bar.sync 1, 64;");
-      if (tid < j) xs[tid] = fma(-s[j * LDS_PAD + tid], xs[j], xs[tid]);
-      asm volatile("bar.sync 1, 64;");
-    }
-  }
-  if (tid < nb) x[tid] = xs[tid];
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// forward update: x[r] -= sum_k L[r][k] xb[k] for r in the rows below the block; 16 lanes per row
-__global__ void __launch_bounds__(256)
-trsv_fwd_update_kernel(const double* __restrict__ Lpanel, long ld, int rows, int nb,
-                       const double* __restrict__ xb, double* __restrict__ x) {
-  __shared__ double sx[BASE];
-  if (threadIdx.x < BASE) sx[threadIdx.x] = threadIdx.x < nb ? xb[threadIdx.x] : 0.0;
-  __syncthreads();
-  const int sub = threadIdx.x & 15;
-  const long r = (long)blockIdx.x * 16 + (threadIdx.x >> 4);
-  double acc = 0.0;
-  if (r < rows) {
-    const double* row = Lpanel + r * ld;
-    for (int k = sub; k < nb; k += 16) acc = fma(row[k], sx[k], acc);
-  }
+template <bool TRANS>
+__global__ void __launch_bounds__(256, 2)
+trsv_persistent_kernel(const double* __restrict__ L, long ld, int n, double* __restrict__ x, int* __restrict__ done) {
+  __shared__ double sD[BASE * LDS_PAD];     // diagonal block (lower part)
+  __shared__ double sR[8][BASE];            // per-warp partial sums
+  __shared__ double sInv[BASE];             // reciprocal diagonal
+  const int nblk = (n + BASE - 1) / BASE;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int ready = 0;                            // blocks known to be final (in solve order)
+  for (int it = blockIdx.x; it < nblk; it += gridDim.x) {
+    const int rb = TRANS ? nblk - 1 - it : it;        // block solved at position `it` of the order
+    const int r0 = rb * BASE;
+    const int nb = min(BASE, n - r0);
+    // diagonal block and reciprocals: independent of x, loaded first
+    {
+      const int c = threadIdx.x & 63;
+      for (int r = threadIdx.x >> 6; r < BASE; r += 4) {
+        double v = (r == c) ? 1.0 : 0.0;
+        if (r < nb && c <= r) v = L[(long)(r0 + r) * ld + r0 + c];
+        sD[r * LDS_PAD + c] = v;
+      }
+    }
+    double acc[8];
 #pragma unroll
-  for (int o = 8; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, 16);
-  if (r < rows && sub == 0) x[r] -= acc;
-}
-
-// backward update: x[c] -= sum_k L[k][c] xb[k] for columns c left of the block; one thread per column
-__global__ void __launch_bounds__(256)
-trsv_bwd_update_kernel(const double* __restrict__ Lrows, long ld, int cols, int nb,
-                       const double* __restrict__ xb, double* __restrict__ x) {
-  __shared__ double sx[BASE];
-  if (threadIdx.x < BASE) sx[threadIdx.x] = threadIdx.x < nb ? xb[threadIdx.x] : 0.0;
-  __syncthreads();
-  const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
-  double acc = 0.0;
-  for (int k = 0; k < nb; ++k) acc = fma(Lrows[(long)k * ld + c], sx[k], acc);
-  x[c] -= acc;
+    for (int k = 0; k < 8; ++k) acc[k] = 0.0;
+    if (!TRANS) {
+      // rows 8 warp .. 8 warp + 7 of the block; lane -> columns 2 lane, 2 lane + 1 of every earlier block
+      const double* rowp[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int r = min(r0 + 8 * warp + k, n - 1);
+        rowp[k] = L + (long)r * ld + 2 * lane;
+      }
+      for (int jb = 0; jb < rb; ++jb) {
+        double2 l[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) l[k] = __ldcs(reinterpret_cast<const double2*>(rowp[k] + jb * BASE));
+        if (jb >= ready) {
+          do { ready = ld_acquire(done); } while (ready <= jb);
+        }
+        const double2 xv = __ldcg(reinterpret_cast<const double2*>(x + jb * BASE + 2 * lane));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { acc[k] = fma(l[k].x, xv.x, acc[k]); acc[k] = fma(l[k].y, xv.y, acc[k]); }
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        double v = acc[k];
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) sR[0][8 * warp + k] = v;
+      }
+    } else {
+      // transposed: rows 8 warp .. 8 warp + 7 of every later block jb; lane -> columns 2 lane, 2 lane + 1 of block rb
+      for (int s = 0; s < it; ++s) {
+        const int jb = nblk - 1 - s;
+        const int nrow = min(BASE, n - jb * BASE);
+        double2 l[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int r = 8 * warp + k;
+          l[k] = (r < nrow) ? __ldcs(reinterpret_cast<const double2*>(L + (long)(jb * BASE + r) * ld + r0 + 2 * lane)) : make_double2(0.0, 0.0);
+        }
+        if (s >= ready) {
+          do { ready = ld_acquire(done); } while (ready <= s);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int r = 8 * warp + k;
+          const double xr = (r < nrow) ? __ldcg(x + jb * BASE + r) : 0.0;
+          acc[0] = fma(l[k].x, xr, acc[0]);
+          acc[1] = fma(l[k].y, xr, acc[1]);
+        }
+      }
+      sR[warp][2 * lane] = acc[0];
+      sR[warp][2 * lane + 1] = acc[1];
+    }
+    __syncthreads();
+    if (warp == 0) {
+      // v = b - (sum of the products); two entries per lane: i = lane, lane + 32
+      double v0, v1;
+      if (!TRANS) {
+        v0 = ((lane < nb) ? x[r0 + lane] : 0.0) - sR[0][lane];
+        v1 = ((lane + 32 < nb) ? x[r0 + lane + 32] : 0.0) - sR[0][lane + 32];
+      } else {
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { s0 += sR[w][lane]; s1 += sR[w][lane + 32]; }
+        v0 = ((lane < nb) ? x[r0 + lane] : 0.0) - s0;
+        v1 = ((lane + 32 < nb) ? x[r0 + lane + 32] : 0.0) - s1;
+      }
+      const double inv0 = 1.0 / sD[lane * LDS_PAD + lane], inv1 = 1.0 / sD[(lane + 32) * LDS_PAD + lane + 32];
+      if (!TRANS) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const double xj = __shfl_sync(0xffffffffu, v0 * inv0, j);
+          if (lane == j) v0 = xj;
+          if (lane > j) v0 = fma(-sD[lane * LDS_PAD + j], xj, v0);
+          v1 = fma(-sD[(lane + 32) * LDS_PAD + j], xj, v1);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const double xj = __shfl_sync(0xffffffffu, v1 * inv1, j);
+          if (lane == j) v1 = xj;
+          if (lane > j) v1 = fma(-sD[(lane + 32) * LDS_PAD + 32 + j], xj, v1);
+        }
+      } else {
+        // L^T x = v: backward over j; v_i -= L[j][i] x_j for i < j
+#pragma unroll
+        for (int j = 31; j >= 0; --j) {
+          const double xj = __shfl_sync(0xffffffffu, v1 * inv1, j);
+          if (lane == j) v1 = xj;
+          if (lane < j) v1 = fma(-sD[(32 + j) * LDS_PAD + 32 + lane], xj, v1);
+          v0 = fma(-sD[(32 + j) * LDS_PAD + lane], xj, v0);
+        }
+#pragma unroll
+        for (int j = 31; j >= 0; --j) {
+          const double xj = __shfl_sync(0xffffffffu, v0 * inv0, j);
+          if (lane == j) v0 = xj;
+          if (lane < j) v0 = fma(-sD[j * LDS_PAD + lane], xj, v0);
+        }
+      }
+      if (lane < nb) x[r0 + lane] = v0;
+      if (lane + 32 < nb) x[r0 + lane + 32] = v1;
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) st_release(done, it + 1);
+    }
+    __syncthreads();    // sD / sR are reused by the next block of this CTA
+  }
 }
 
 }  // namespace
@@ -490,27 +573,25 @@ int inverse_interior(gpp_handle* h, GramSlot& s) {
 }
 
 int trsv_lower(gpp_handle* h, const double* L, long ld, int n, double* x, bool transposed) {
-  if (!transposed) {
-    for (int j0 = 0; j0 < n; j0 += BASE) {
-      const int nb = (n - j0 < BASE) ? (n - j0) : BASE;
-      trsv_diag_kernel<<<1, 256, 0, h->cur>>>(L + (long)j0 * ld + j0, ld, nb, x + j0, 0);
-      const int rows = n - j0 - nb;
-      if (rows > 0)
-        trsv_fwd_update_kernel<<<(rows + 15) / 16, 256, 0, h->cur>>>(L + (long)(j0 + nb) * ld + j0, ld, rows, nb,
-                                                                         x + j0, x + j0 + nb);
-      h->launches += 2;
-    }
-  } else {
-    const int nblk = (n + BASE - 1) / BASE;
-    for (int b = nblk - 1; b >= 0; --b) {
-      const int j0 = b * BASE;
-      const int nb = (n - j0 < BASE) ? (n - j0) : BASE;
-      trsv_diag_kernel<<<1, 256, 0, h->cur>>>(L + (long)j0 * ld + j0, ld, nb, x + j0, 1);
-      if (j0 > 0)
-        trsv_bwd_update_kernel<<<(j0 + 255) / 256, 256, 0, h->cur>>>(L + (long)j0 * ld, ld, j0, nb, x + j0, x);
-      h->launches += 2;
-    }
+  if (n <= 0) return GPP_OK;
+  if ((ld & 1) || (reinterpret_cast<uintptr_t>(L) & 15) || (reinterpret_cast<uintptr_t>(x) & 15)) { h->err = "trsv: operands must be 16-byte aligned"; return -1; }
+  static int grid_cap[64] = {0};
+  int cap = h->device < 64 ? grid_cap[h->device] : 0;
+  if (!cap) {
+    int per_sm = 0, sms = 0;
+    CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trsv_persistent_kernel<false>, 256, 0));
+    CUDA_TRY(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+    cap = (per_sm > 0 ? per_sm : 1) * sms;
+    if (h->device < 64) grid_cap[h->device] = cap;
   }
+  if (!h->d_trsv_flag) CUDA_TRY(h, cudaMalloc(&h->d_trsv_flag, 16 * sizeof(int)));
+  int* flag = h->d_trsv_flag + (h->trsv_calls++ & 15);
+  CUDA_TRY(h, cudaMemsetAsync(flag, 0, sizeof(int), h->cur));
+  const int nblk = (n + BASE - 1) / BASE;
+  const int grid = nblk < cap ? nblk : cap;
+  if (transposed) trsv_persistent_kernel<true><<<grid, 256, 0, h->cur>>>(L, ld, n, x, flag);
+  else trsv_persistent_kernel<false><<<grid, 256, 0, h->cur>>>(L, ld, n, x, flag);
+  h->launches++;
   CUDA_TRY(h, cudaGetLastError());
   return GPP_OK;
 }

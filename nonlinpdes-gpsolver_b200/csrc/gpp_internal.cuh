@@ -108,6 +108,8 @@ struct gpp_handle {
   GramSlot slot[GPP_MAX_SLOTS];
   GnState gn;
   int* d_info = nullptr;      // device flag: first failed pivot (1-based) or 0
+  int* d_trsv_flag = nullptr; // progress counters of the persistent triangular solves (ring of 16)
+  unsigned trsv_calls = 0;
   double* work = nullptr;     // scratch (panel copies)
   size_t work_bytes = 0;
   int NB = 512;               // block-column width of the blocked factorisations
