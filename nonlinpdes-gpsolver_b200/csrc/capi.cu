@@ -136,6 +136,7 @@ int gpp_destroy(gpp_handle* h) {
   if (h->work) cudaFree(h->work);
   if (h->d_info) cudaFree(h->d_info);
   if (h->d_trsv_flag) cudaFree(h->d_trsv_flag);
+  if (h->d_bar) cudaFree(h->d_bar);
   for (auto& e : h->ev) cudaEventDestroy(e);
   for (auto& e : h->evpool) cudaEventDestroy(e);
   if (h->sP) cudaStreamDestroy(h->sP);
@@ -157,6 +158,9 @@ int gpp_set_option(gpp_handle* h, const char* name, double value) {
     return GPP_OK;
   }
   if (!strcmp(name, "lookahead")) { h->lookahead = value != 0.0; return GPP_OK; }
+  if (!strcmp(name, "tiled_potrf")) { h->tiled_potrf = value != 0.0; return GPP_OK; }
+  if (!strcmp(name, "tiled_max_n")) { h->tiled_max_n = (int)value; return GPP_OK; }
+  if (!strcmp(name, "tiled_grid_limit")) { h->tiled_grid_limit = (int)value; return GPP_OK; }
   if (!strcmp(name, "gemm_tile")) {
     const int t = (int)value;
     if (t != 0 && t != 64 && t != 128) { h->err = "gemm_tile must be 0, 64 or 128"; return -3; }

@@ -118,6 +118,251 @@ trsm_base_kernel(double* __restrict__ P, long ldp, const TrsmRows rm, const doub
   }
 }
 
+// ---------------------------------------------------------------------------
+// Tiled right-looking Cholesky of a whole (small) matrix in ONE persistent kernel: n <= a few thousand, 64 x 64 tiles.
+// The blocked path above needs ~50 dependent launches per 512-wide block column; for the latency-bound configurations
+// (BASELINE C1-C4: M ~ 2000-4200, n ~ 900-3000) and for the diagonal blocks of the large factorisations that launch
+// chain IS the run time.  Here all CTAs are resident and meet at a global barrier (atomic counter, release / acquire):
+//   step k:  B(k): tiles (i, k), i > k, solved against the factored diagonal tile  X L_kk^T = A_ik     | barrier
+//            C(k): tiles (i, j), k < j <= i:  A_ij -= L_ik L_jk^T (entry by entry in k order: progressive
+//                  accumulation); the CTA that updates tile (k+1, k+1) factors it right away  | barrier
+// Tile data goes through L2 (ld.cg) because other CTAs rewrite it between phases.
+// ---------------------------------------------------------------------------
+constexpr int TT = 64;             // tile edge
+constexpr int TPAD = 66;           // k-major operand tiles: row stride (doubles), 16-byte aligned rows
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    while (ld_acquire_u32(bar) < target) { }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// Factor the tile held row-wise in shared memory (st[r * LDS_PAD + c], lower part valid, nb x nb; rows >= nb are treated
+// as identity rows).  Threads 0..63 own one row each; called by the whole CTA (block barriers inside).  The 64 columns are
+// processed in two passes of 32 so that a thread keeps 32 doubles in registers; per entry the operation sequence is that
+// of potrf_base_kernel (updates applied one by one in column order).
+__device__ __forceinline__ void tile_potrf_smem(double* st, double* col, double* sdiag, int nb, int gidx0, int* info) {
+  const int i = threadIdx.x;
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    const int c0 = 32 * pass;
+    double a[32];
+    if (i < TT) {
+#pragma unroll
+      for (int k = 0; k < 32; ++k) a[k] = (i < nb && c0 + k <= i) ? st[i * LDS_PAD + c0 + k] : (c0 + k == i ? 1.0 : 0.0);
+      if (pass == 1) {
+        // entries (i, 32..63) receive the updates of columns 0..31 first
+#pragma unroll 4
+        for (int j = 0; j < 32; ++j) {
+          const double lij = (i < nb) ? st[i * LDS_PAD + j] : 0.0;
+#pragma unroll
+          for (int k = 0; k < 32; ++k) a[k] = fma(-lij, st[(32 + k) * LDS_PAD + j], a[k]);
+        }
+      }
+    }
+#pragma unroll
+    for (int jj = 0; jj < 32; ++jj) {
+      const int j = c0 + jj;
+      if (i == j) {
+        const double d = a[jj];
+        if (!(d > 0.0) && j < nb) atomicCAS(info, 0, gidx0 + j + 1);
+        const double sq = sqrt(d);
+        a[jj] = sq;
+        *sdiag = sq;
+      }
+      __syncthreads();
+      double l = 0.0;
+      if (i < TT) {
+        if (i > j) { l = a[jj] / *sdiag; a[jj] = l; }
+        col[i] = l;
+      }
+      __syncthreads();
+      if (i < TT) {
+#pragma unroll
+        for (int k = jj + 1; k < 32; ++k) a[k] = fma(-l, col[c0 + k], a[k]);
+      }
+    }
+    if (i < TT) {
+#pragma unroll
+      for (int k = 0; k < 32; ++k) st[i * LDS_PAD + c0 + k] = a[k];
+    }
+    __syncthreads();
+  }
+}
+
+// rows of st (row-major, threads 0..63 one row each) solved against the transposed factor in sLt (sLt[j * TPAD + k] =
+// L[k][j], identity-padded): X L^T = P in place, two passes of 32 columns; operation sequence of trsm_base_kernel
+__device__ __forceinline__ void tile_trsm_smem(double* st, const double* sLt) {
+  const int tid = threadIdx.x;
+  if (tid >= TT) return;
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    const int c0 = 32 * pass;
+    double x[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) x[k] = st[tid * LDS_PAD + c0 + k];
+    if (pass == 1) {
+#pragma unroll 4
+      for (int j = 0; j < 32; ++j) {
+        const double xj = st[tid * LDS_PAD + j];
+        const double* lc = sLt + j * TPAD + 32;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) x[k] = fma(-xj, lc[k], x[k]);
+      }
+    }
+#pragma unroll
+    for (int jj = 0; jj < 32; ++jj) {
+      const double* lc = sLt + (c0 + jj) * TPAD + c0;
+      const double xj = x[jj] / lc[jj];
+      x[jj] = xj;
+#pragma unroll
+      for (int k = jj + 1; k < 32; ++k) x[k] = fma(-xj, lc[k], x[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 32; ++k) st[tid * LDS_PAD + c0 + k] = x[k];
+  }
+}
+
+__global__ void __launch_bounds__(256, 1)
+potrf_tiled_kernel(double* __restrict__ A, long ld, int n, int gidx0, int* info, unsigned* bar) {
+  extern __shared__ double tsm[];
+  double* sAt = tsm;                       // [TT][TPAD]  operand tile, k-major: sAt[kk * TPAD + r]
+  double* sBt = tsm + TT * TPAD;           // [TT][TPAD]
+  double* st = tsm + 2 * TT * TPAD;        // [TT][LDS_PAD] row-major tile (diagonal factor / solve staging)
+  double* col = st + TT * LDS_PAD;         // [TT]
+  double* sdiag = col + TT;
+  const int tid = threadIdx.x;
+  const int G = gridDim.x;
+  const int nt = (n + TT - 1) / TT;
+  unsigned phase = 0;
+  auto rows_of_tile = [&](int t) { return min(TT, n - t * TT); };
+
+  // tile (0, 0) is factored by CTA 0 before the first barrier
+  if (blockIdx.x == 0) {
+    const int nb = rows_of_tile(0);
+    for (int e = tid; e < TT * TT; e += 256) {
+      const int r = e / TT, c = e % TT;
+      st[r * LDS_PAD + c] = (r < nb && c <= r) ? __ldcg(A + (long)r * ld + c) : 0.0;
+    }
+    __syncthreads();
+    tile_potrf_smem(st, col, sdiag, nb, gidx0, info);
+    for (int e = tid; e < TT * TT; e += 256) {
+      const int r = e / TT, c = e % TT;
+      if (r < nb && c <= r) A[(long)r * ld + c] = st[r * LDS_PAD + c];
+    }
+  }
+  grid_barrier(bar, (++phase) * G);
+
+  for (int k = 0; k < nt; ++k) {
+    const int k0 = k * TT, nbk = rows_of_tile(k);
+    // ---- B(k): solve the tiles below the diagonal tile
+    if (k + 1 < nt) {
+      // L_kk transposed into sAt (sAt[j * TPAD + kk] = L[kk][j]), padded with the identity
+      bool have_l = false;
+      for (int i = k + 1 + blockIdx.x; i < nt; i += G) {
+        if (!have_l) {
+          for (int e = tid; e < TT * TT; e += 256) {
+            const int r = e / TT, c = e % TT;      // L[r][c]
+            double v = (r == c) ? 1.0 : 0.0;
+            if (r < nbk && c < nbk) v = (c <= r) ? __ldcg(A + (long)(k0 + r) * ld + k0 + c) : 0.0;
+            sAt[c * TPAD + r] = v;
+          }
+          have_l = true;
+        }
+        const int i0 = i * TT, nbi = rows_of_tile(i);
+        for (int e = tid; e < TT * TT; e += 256) {
+          const int r = e / TT, c = e % TT;
+          st[r * LDS_PAD + c] = (r < nbi && c < nbk) ? __ldcg(A + (long)(i0 + r) * ld + k0 + c) : 0.0;
+        }
+        __syncthreads();
+        tile_trsm_smem(st, sAt);
+        __syncthreads();
+        for (int e = tid; e < TT * TT; e += 256) {
+          const int r = e / TT, c = e % TT;
+          if (r < nbi && c < nbk) A[(long)(i0 + r) * ld + k0 + c] = st[r * LDS_PAD + c];
+        }
+        __syncthreads();
+      }
+    }
+    grid_barrier(bar, (++phase) * G);
+    if (k + 1 >= nt) break;
+    // ---- C(k): trailing update; linear index t over the lower-triangular tile set starting at (k+1, k+1)
+    const int m = nt - k - 1;
+    const long ntile = (long)m * (m + 1) / 2;
+    for (long t = blockIdx.x; t < ntile; t += G) {
+      int ii = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+      while ((long)(ii + 1) * (ii + 2) / 2 <= t) ++ii;
+      while ((long)ii * (ii + 1) / 2 > t) --ii;
+      const int jj = (int)(t - (long)ii * (ii + 1) / 2);
+      const int ti = k + 1 + ii, tj = k + 1 + jj;
+      const int i0 = ti * TT, j0 = tj * TT, nbi = rows_of_tile(ti), nbj = rows_of_tile(tj);
+      // operand tiles, k-major
+      for (int e = tid; e < TT * TT; e += 256) {
+        const int r = e / TT, c = e % TT;
+        sAt[c * TPAD + r] = (r < nbi && c < nbk) ? __ldcg(A + (long)(i0 + r) * ld + k0 + c) : 0.0;
+        sBt[c * TPAD + r] = (r < nbj && c < nbk) ? __ldcg(A + (long)(j0 + r) * ld + k0 + c) : 0.0;
+      }
+      const int ty = tid >> 4, tx = tid & 15;
+      double acc[4][4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int gr = ty * 4 + r, gc = tx * 4 + c;
+          acc[r][c] = (gr < nbi && gc < nbj) ? __ldcg(A + (long)(i0 + gr) * ld + j0 + gc) : 0.0;
+        }
+      __syncthreads();
+#pragma unroll 8
+      for (int kk = 0; kk < TT; ++kk) {
+        const double2 a01 = *reinterpret_cast<const double2*>(sAt + kk * TPAD + ty * 4);
+        const double2 a23 = *reinterpret_cast<const double2*>(sAt + kk * TPAD + ty * 4 + 2);
+        const double2 b01 = *reinterpret_cast<const double2*>(sBt + kk * TPAD + tx * 4);
+        const double2 b23 = *reinterpret_cast<const double2*>(sBt + kk * TPAD + tx * 4 + 2);
+        const double a[4] = {a01.x, a01.y, a23.x, a23.y};
+        const double b[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc[r][c] = fma(-a[r], b[c], acc[r][c]);
+      }
+      if (ti == tj && ii == 0) {
+        // the next diagonal tile: factor it now (its column is solved right after the barrier)
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) st[(ty * 4 + r) * LDS_PAD + tx * 4 + c] = acc[r][c];
+        __syncthreads();
+        tile_potrf_smem(st, col, sdiag, nbi, gidx0 + i0, info);
+        for (int e = tid; e < TT * TT; e += 256) {
+          const int r = e / TT, c = e % TT;
+          if (r < nbi && c <= r) A[(long)(i0 + r) * ld + j0 + c] = st[r * LDS_PAD + c];
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int gr = ty * 4 + r, gc = tx * 4 + c;
+            if (gr < nbi && gc < nbj && (ti != tj || gc <= gr)) A[(long)(i0 + gr) * ld + j0 + gc] = acc[r][c];
+          }
+      }
+      __syncthreads();
+    }
+    grid_barrier(bar, (++phase) * G);
+  }
+}
+constexpr int TILED_SMEM = (2 * TT * TPAD + TT * LDS_PAD + TT + 8) * 8;
+
 __global__ void fill_identity_kernel(double* __restrict__ A, long ld, int rows, int cols) {
   long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e < (long)rows * cols) {
@@ -169,7 +414,6 @@ __global__ void __launch_bounds__(256, 2)
 trsv_persistent_kernel(const double* __restrict__ L, long ld, int n, double* __restrict__ x, int* __restrict__ done) {
   __shared__ double sD[BASE * LDS_PAD];     // diagonal block (lower part)
   __shared__ double sR[8][BASE];            // per-warp partial sums
-  __shared__ double sInv[BASE];             // reciprocal diagonal
   const int nblk = (n + BASE - 1) / BASE;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int ready = 0;                            // blocks known to be final (in solve order)
@@ -342,7 +586,33 @@ int trsm_right_lt(gpp_handle* h, const Mat& P, int pr0, int pc0, int rows, const
   return trsm_right_lt(h, P, pr0, pc0 + hh, rows, L, lr0 + hh, lc0 + hh, nb - hh);
 }
 
+// whole-matrix tiled factorisation (one persistent launch) of the nb x nb block at (r0, c0)
+static int potrf_tiled(gpp_handle* h, const Mat& A, int r0, int c0, int nb, int gidx0) {
+  static int grid_cap[64] = {0};
+  int cap = h->device < 64 ? grid_cap[h->device] : 0;
+  if (!cap) {
+    CUDA_TRY(h, cudaFuncSetAttribute(potrf_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TILED_SMEM));
+    int per_sm = 0, sms = 0;
+    CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, potrf_tiled_kernel, 256, TILED_SMEM));
+    CUDA_TRY(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+    cap = (per_sm > 0 ? per_sm : 1) * sms;
+    if (h->device < 64) grid_cap[h->device] = cap;
+  }
+  if (!h->d_bar) CUDA_TRY(h, cudaMalloc(&h->d_bar, 64 * sizeof(unsigned)));
+  unsigned* bar = h->d_bar + (h->bar_calls++ & 63);
+  CUDA_TRY(h, cudaMemsetAsync(bar, 0, sizeof(unsigned), h->cur));
+  const int nt = (nb + TT - 1) / TT;
+  const long tiles = (long)nt * (nt - 1) / 2;          // largest trailing update
+  int grid = (int)(tiles < 1 ? 1 : (tiles < cap ? tiles : cap));
+  if (h->tiled_grid_limit > 0 && grid > h->tiled_grid_limit) grid = h->tiled_grid_limit;
+  potrf_tiled_kernel<<<grid, 256, TILED_SMEM, h->cur>>>(A.base + (long)r0 * A.ld + c0, A.ld, nb, gidx0, h->d_info, bar);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return GPP_OK;
+}
+
 int potrf_diag(gpp_handle* h, const Mat& A, int r0, int c0, int nb, int gidx0) {
+  if (nb > BASE && h->tiled_potrf) return potrf_tiled(h, A, r0, c0, nb, gidx0);
   if (nb <= BASE) {
     potrf_base_kernel<<<1, BASE, 0, h->cur>>>(A.base + (long)r0 * A.ld + c0, A.ld, nb, gidx0, h->d_info);
     h->launches++;
@@ -388,6 +658,7 @@ int potrf_lower(gpp_handle* h, double* A, long ld, int n, const TMap2* map) {
   const int NB = h->NB;
   const int nblk = (n + NB - 1) / NB;
   CUDA_TRY(h, cudaMemsetAsync(h->d_info, 0, sizeof(int), h->stream));
+  if (h->tiled_potrf && n <= h->tiled_max_n) return potrf_tiled(h, M, 0, 0, n, 0);   // latency-bound sizes: one persistent kernel
   auto update = [&](int j0, int nbj, int k0, int k1) -> int {
     if (k1 <= k0) return GPP_OK;
     GemmDesc d{};

@@ -471,12 +471,24 @@ int dist_potrf_matrix(gpp_handle* h, DistState* d, double* A, long ld, int n, co
     CUDA_TRY(h, cudaStreamWaitEvent(Sp, ev0, 0));
     CUDA_TRY(h, cudaStreamWaitEvent(Sb, ev0, 0));
     std::vector<cudaEvent_t> ev_panel(nblk), ev_a(nblk);
+    // GPP_TRACE: timed events around the pieces of the panel chain of every 16th column (Sp is the critical path once
+    // the bulk of a step is shorter than the chain)
+    static const bool trace = getenv("GPP_TRACE") != nullptr;
+    struct ChainEv { int j; cudaEvent_t e[6]; };
+    std::vector<ChainEv> chain;
+    auto tmark = [&](ChainEv* c, int k) { if (c) { cudaEventCreate(&c->e[k]); cudaEventRecord(c->e[k], Sp); } };
+    ChainEv* cur_chain = nullptr;
     auto panel = [&](int j) -> int {          // on Sp: factorise, broadcast, solve, gather column j
       h->cur = Sp;
+      tmark(cur_chain, 1);
       int r = panel_factor(g, j);
+      tmark(cur_chain, 2);
       if (!r) r = bcast_diag(h, d, A, ld, n, NB, j, Sp);
+      tmark(cur_chain, 3);
       if (!r) r = panel_solve(pl, j);
+      tmark(cur_chain, 4);
       if (!r) r = gather_panel(h, d, A, ld, n, NB, j, j + 1, nblk, Sp);
+      tmark(cur_chain, 5);
       return r;
     };
     rc = panel(0);
@@ -487,8 +499,12 @@ int dist_potrf_matrix(gpp_handle* h, DistState* d, double* A, long ld, int n, co
         // look-ahead: column j+1 first (it has all updates of the panels < j once bulkA(j-1) is done), then its panel chain
         if (j >= 1) CUDA_TRY(h, cudaStreamWaitEvent(Sp, ev_a[j - 1], 0));
         h->cur = Sp;
+        cur_chain = nullptr;
+        if (trace && d->rank == 0 && (j + 1) % 16 == 0) { chain.push_back(ChainEv{j + 1, {}}); cur_chain = &chain.back(); }
+        tmark(cur_chain, 0);
         rc = run_tasks(h, pl, pl.la[j], Am, Am, Am, NB, -1.0, true);
         if (!rc) rc = panel(j + 1);
+        cur_chain = nullptr;
         if (rc) break;
       }
       CUDA_TRY(h, cudaStreamWaitEvent(Sb, ev_panel[j], 0));
@@ -505,6 +521,16 @@ int dist_potrf_matrix(gpp_handle* h, DistState* d, double* A, long ld, int n, co
     CUDA_TRY(h, cudaEventRecord(e2, Sb));
     CUDA_TRY(h, cudaStreamWaitEvent(S, e1, 0));
     CUDA_TRY(h, cudaStreamWaitEvent(S, e2, 0));
+    if (!chain.empty()) {
+      cudaStreamSynchronize(S);
+      for (ChainEv& c : chain) {
+        float t[5];
+        for (int k = 0; k < 5; ++k) cudaEventElapsedTime(&t[k], c.e[k], c.e[k + 1]);
+        fprintf(stderr, "[gpp trace] panel chain n=%d column %d/%d: look-ahead update %.3f ms | diag potrf %.3f | diag bcast %.3f | panel solve %.3f | gather %.3f\n",
+                n, c.j, nblk, t[0], t[1], t[2], t[3], t[4]);
+        for (int k = 0; k < 6; ++k) cudaEventDestroy(c.e[k]);
+      }
+    }
   }
   h->cur = S;
   if (want_info) {

@@ -110,6 +110,11 @@ struct gpp_handle {
   int* d_info = nullptr;      // device flag: first failed pivot (1-based) or 0
   int* d_trsv_flag = nullptr; // progress counters of the persistent triangular solves (ring of 16)
   unsigned trsv_calls = 0;
+  unsigned* d_bar = nullptr;  // global-barrier counters of the persistent tiled Cholesky (ring of 64)
+  unsigned bar_calls = 0;
+  int tiled_potrf = 1;        // use the persistent tiled kernel for diagonal blocks and small matrices
+  int tiled_max_n = 4608;     // largest matrix factored whole by the tiled kernel
+  int tiled_grid_limit = 0;   // tests / tuning: cap on its grid size (0 = resident capacity)
   double* work = nullptr;     // scratch (panel copies)
   size_t work_bytes = 0;
   int NB = 512;               // block-column width of the blocked factorisations

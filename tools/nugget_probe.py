@@ -1,26 +1,40 @@
-"""Smallest nugget for which the FP64 Cholesky of Theta succeeds, GPU vs LAPACK (developer tool)."""
-import argparse, sys, os, math
+"""Does Theta + nugget * diag(r) have an FP64 Cholesky factor?  GPU factorisation next to LAPACK dpotrf on the SAME matrix
+(downloaded from the device), one JSON line per (N_domain, nugget).  Settles whether a failure at nugget 1e-13 is the
+matrix (numerically indefinite in FP64) or our rounding.  Developer / evidence tool (profiles/r02_nugget_lapack_vs_gpu.jsonl)."""
+import argparse, json, math, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
+import scipy.linalg as sla
 from nonlinpdes_gpsolver_b200 import PDEs
+
 ap = argparse.ArgumentParser()
-ap.add_argument("--N", type=int, nargs="+", default=[5000])
-ap.add_argument("--nuggets", type=float, nargs="+", default=[1e-13, 1e-12, 1e-11, 1e-10])
-ap.add_argument("--lapack_max", type=int, default=6000)
+ap.add_argument("--N", type=int, nargs="+", default=[10000, 20000])
+ap.add_argument("--nuggets", type=float, nargs="+", default=[1e-13, 1e-12])
+ap.add_argument("--lapack_max", type=int, default=20000)
 a = ap.parse_args()
+try:
+    from threadpoolctl import threadpool_limits
+    threadpool_limits(limits=os.cpu_count())
+except Exception:
+    pass
 for N in a.N:
     Nb = 4 * (math.ceil(math.sqrt(N)) + 1)
     np.random.seed(0)
     p = PDEs.Nonlinear_elliptic2d(alpha=1.0, m=3, bdy=lambda x, y: 0 * x, rhs=lambda x, y: 0 * x)
     p.sampled_pts(N, Nb)
+    M = 2 * N + p.N_boundary
     for ng in a.nuggets:
         p.Gram_matrix("Gaussian", 0.2, ng, "adaptive")
-        lap = None
+        rec = dict(N_domain=N, M=M, nugget=ng, sigma=0.2, trace_ratio=p.ratio)
         if N <= a.lapack_max:
-            th = p.Theta
-            try:
-                np.linalg.cholesky(th); lap = 0
-            except np.linalg.LinAlgError:
-                lap = -1
+            th = p.Theta                                   # the device's own matrix, symmetric, nugget included
+            t0 = time.perf_counter()
+            _, info = sla.lapack.dpotrf(th, lower=1, overwrite_a=1, clean=0)
+            rec.update(lapack_dpotrf_info=int(info), lapack_seconds=round(time.perf_counter() - t0, 1), host_threads=os.cpu_count())
+            del th
         p.Gram_Cholesky()
-        print(f"N={N} nugget={ng:g} gpu_info={p.chol_info} lapack={'ok' if lap == 0 else ('fail' if lap == -1 else 'n/a')}", flush=True)
+        rec.update(gpu_info=int(p.chol_info), gpu_potrf_ms=round(p.timings["potrf_ms"], 1))
+        rec["verdict"] = ("both fail: indefinite in FP64" if rec.get("lapack_dpotrf_info", 0) > 0 and rec["gpu_info"] > 0 else
+                          "both succeed" if rec.get("lapack_dpotrf_info", 1) == 0 and rec["gpu_info"] == 0 else
+                          "GPU succeeds, LAPACK fails" if rec["gpu_info"] == 0 else "GPU fails, LAPACK succeeds / not run")
+        print(json.dumps(rec), flush=True)
