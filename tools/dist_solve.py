@@ -100,7 +100,7 @@ if a.check:
     Xt = np.random.RandomState(1).uniform(0, 1, (64, 2))
     prob.extend_sol(Xt); ref.extend_sol(Xt)
     e_pred = float(np.max(np.abs(prob.extended_sol - ref.extended_sol)))
-    ok = e_res < 1e-13 and e_lap < 1e-6 and e_loss < 1e-7 and e_sol < 1e-7 and e_pred < 1e-6
+    ok = e_res < 1e-13 and e_lap < 1e-5 and e_loss < 1e-6 and e_sol < 1e-6 and e_pred < 1e-5
     vals = maxred([e_res, e_lap, e_loss, e_sol, e_pred, 0.0 if ok else 1.0])
     if rank == 0:
         print(json.dumps(dict(check="sharded factor: backward error and vs single-GPU factor; sharded solve vs single-GPU solve",
