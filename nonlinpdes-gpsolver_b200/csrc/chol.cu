@@ -363,6 +363,85 @@ potrf_tiled_kernel(double* __restrict__ A, long ld, int n, int gidx0, int* info,
 }
 constexpr int TILED_SMEM = (2 * TT * TPAD + TT * LDS_PAD + TT + 8) * 8;
 
+// ---------------------------------------------------------------------------
+// Fused panel solve  X L^T = P  (in place), L = nbw x nbw lower (nbw <= NB), P = rows x nbw, rows contiguous or
+// block-cyclic (TrsmRows).  ONE launch: a CTA owns 64 rows and sweeps the 64-wide column blocks cb = 0, 1, ...:
+//   T = P[:, cb] - sum_{c < cb} X[:, c] L[cb, c]^T  (64^3 tile products, FP64 FMA from shared memory), then the
+//   64 x 64 substitution against L[cb, cb].  CTAs never wait for each other.
+// Used on the critical path of the sharded factorisations (csrc/dist.cu), where the recursive solve costs ~15
+// dependent launches per column, each waiting for an SM of the concurrently running trailing update.
+// Per entry the updates are applied one by one in column order (the rounding model of the recursive path).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 1)
+trsm_panel_kernel(double* __restrict__ P, long ldp, const TrsmRows rm, const double* __restrict__ L, long ldl, int nbw) {
+  extern __shared__ double tsm[];
+  double* sAt = tsm;                       // [TT][TPAD] X tile (k-major) / transposed diagonal factor
+  double* sBt = tsm + TT * TPAD;           // [TT][TPAD] L[cb, c] tile (k-major)
+  double* st = tsm + 2 * TT * TPAD;        // [TT][LDS_PAD] row-major staging of the tile being solved
+  const int tid = threadIdx.x;
+  const int r0 = blockIdx.x * TT;          // logical first row
+  const int nrow = min(TT, rm.rows - r0);
+  const int ncb = (nbw + TT - 1) / TT;
+  const int ty = tid >> 4, tx = tid & 15;
+  // physical rows of this CTA's 64 logical rows (a 64-row tile never straddles a cyclic block: nb % 64 == 0)
+  const long prow0 = trsm_phys_row(rm, r0);
+  double* Pt = P + prow0 * ldp;
+  for (int cb = 0; cb < ncb; ++cb) {
+    const int c0 = cb * TT, wcb = min(TT, nbw - c0);
+    double acc[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int gr = ty * 4 + r, gc = tx * 4 + c;
+        acc[r][c] = (gr < nrow && gc < wcb) ? Pt[(long)gr * ldp + c0 + gc] : 0.0;
+      }
+    for (int cc = 0; cc < cb; ++cc) {
+      const int k0 = cc * TT;              // all earlier column blocks are full (64 wide)
+      for (int e = tid; e < TT * TT; e += 256) {
+        const int r = e / TT, c = e % TT;
+        sAt[c * TPAD + r] = (r < nrow) ? Pt[(long)r * ldp + k0 + c] : 0.0;                 // X[:, cc] (already solved)
+        sBt[c * TPAD + r] = (r < wcb) ? L[(long)(c0 + r) * ldl + k0 + c] : 0.0;            // L[cb, cc]
+      }
+      __syncthreads();
+#pragma unroll 8
+      for (int kk = 0; kk < TT; ++kk) {
+        const double2 a01 = *reinterpret_cast<const double2*>(sAt + kk * TPAD + ty * 4);
+        const double2 a23 = *reinterpret_cast<const double2*>(sAt + kk * TPAD + ty * 4 + 2);
+        const double2 b01 = *reinterpret_cast<const double2*>(sBt + kk * TPAD + tx * 4);
+        const double2 b23 = *reinterpret_cast<const double2*>(sBt + kk * TPAD + tx * 4 + 2);
+        const double a[4] = {a01.x, a01.y, a23.x, a23.y};
+        const double b[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc[r][c] = fma(-a[r], b[c], acc[r][c]);
+      }
+      __syncthreads();
+    }
+    // diagonal factor L[cb, cb] transposed (identity padded) and the tile to solve
+    for (int e = tid; e < TT * TT; e += 256) {
+      const int r = e / TT, c = e % TT;    // L[r][c]
+      double v = (r == c) ? 1.0 : 0.0;
+      if (r < wcb && c < wcb) v = (c <= r) ? L[(long)(c0 + r) * ldl + c0 + c] : 0.0;
+      sAt[c * TPAD + r] = v;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) st[(ty * 4 + r) * LDS_PAD + tx * 4 + c] = acc[r][c];
+    __syncthreads();
+    tile_trsm_smem(st, sAt);
+    __syncthreads();
+    for (int e = tid; e < TT * TT; e += 256) {
+      const int r = e / TT, c = e % TT;
+      if (r < nrow && c < wcb) Pt[(long)r * ldp + c0 + c] = st[r * LDS_PAD + c];
+    }
+    __syncthreads();      // the solved tile is read back (as X[:, cb]) by other threads of this CTA in the next sweep
+  }
+}
+constexpr int PANEL_SMEM = (2 * TT * TPAD + TT * LDS_PAD) * 8;
+
 __global__ void fill_identity_kernel(double* __restrict__ A, long ld, int rows, int cols) {
   long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e < (long)rows * cols) {
@@ -550,6 +629,20 @@ int trsm_base_launch(gpp_handle* h, double* P, long ldp, const TrsmRows& rm, con
     if (h->device < 64) attr[h->device] = true;
   }
   trsm_base_kernel<<<(rm.rows + TRSM_ROWS - 1) / TRSM_ROWS, TRSM_ROWS, smem, h->cur>>>(P, ldp, rm, L, ldl, nbl);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return GPP_OK;
+}
+
+int trsm_panel_launch(gpp_handle* h, double* P, long ldp, const TrsmRows& rm, const double* L, long ldl, int nbw) {
+  if (rm.rows <= 0 || nbw <= 0) return GPP_OK;
+  if (rm.stride_blk != 0 && rm.nb % TT) { h->err = "trsm_panel: cyclic block size must be a multiple of 64"; return -1; }
+  static bool attr[64] = {false};
+  if (h->device >= 64 || !attr[h->device]) {
+    CUDA_TRY(h, cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM));
+    if (h->device < 64) attr[h->device] = true;
+  }
+  trsm_panel_kernel<<<(rm.rows + TT - 1) / TT, 256, PANEL_SMEM, h->cur>>>(P, ldp, rm, L, ldl, nbw);
   h->launches++;
   CUDA_TRY(h, cudaGetLastError());
   return GPP_OK;

@@ -443,6 +443,8 @@ int dist_potrf_matrix(gpp_handle* h, DistState* d, double* A, long ld, int n, co
     return potrf_diag(h, Amat, j * NB, j * NB, rows_of(n, NB, j), j * NB);
   };
   auto panel_solve = [&](const Plan& pl, int j) -> int {
+    if (pl.rows[j].rows <= h->fused_trsm_rows)      // one launch; the recursion pays ~15 launches under SM contention
+      return trsm_panel_launch(h, A + (long)j * NB, ld, pl.rows[j], A + (long)j * NB * ld + (long)j * NB, ld, rows_of(n, NB, j));
     size_t next = 0;
     return exec_trsm(h, pl, pl.trsm[j], next, pl.rows[j], Am, j * NB, Am, j * NB, j * NB, rows_of(n, NB, j), NB);
   };
@@ -565,9 +567,11 @@ int dist_uinv(gpp_handle* h, DistState* d, GramSlot& s) {
     const int i0 = i * NB, nbi = rows_of(n, NB, i);
     int r = GPP_OK;
     if (owner_of(g, i, i) == g.p * g.Q + g.q) r = fill_identity_launch(h, d->U + (long)i0 * s.ld + i0, s.ld, nbi, nbi);
+    if (r) return r;
+    if (pl.rows[i].rows <= h->fused_trsm_rows)
+      return trsm_panel_launch(h, d->U + i0, s.ld, pl.rows[i], s.T + (long)i0 * s.ld + i0, s.ld, nbi);
     size_t next = 0;
-    if (!r) r = exec_trsm(h, pl, pl.trsm[i], next, pl.rows[i], Um, i0, Tm, i0, i0, nbi, NB);
-    return r;
+    return exec_trsm(h, pl, pl.trsm[i], next, pl.rows[i], Um, i0, Tm, i0, i0, nbi, NB);
   };
 
   if (d->nv > 0) {

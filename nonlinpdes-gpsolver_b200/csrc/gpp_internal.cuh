@@ -115,6 +115,7 @@ struct gpp_handle {
   int tiled_potrf = 1;        // use the persistent tiled kernel for diagonal blocks and small matrices
   int tiled_max_n = 4608;     // largest matrix factored whole by the tiled kernel
   int tiled_grid_limit = 0;   // tests / tuning: cap on its grid size (0 = resident capacity)
+  int fused_trsm_rows = 65536; // sharded path: panels with at most this many own rows use the one-launch panel solve
   double* work = nullptr;     // scratch (panel copies)
   size_t work_bytes = 0;
   int NB = 512;               // block-column width of the blocked factorisations
@@ -219,6 +220,8 @@ struct TrsmRows {
 };
 // 64-wide base case of the panel solve X L^T = P (in place), L = nbl x nbl lower block; P points at column 0 of the panel
 int trsm_base_launch(gpp_handle* h, double* P, long ldp, const TrsmRows& rm, const double* L, long ldl, int nbl);
+// the same solve for the whole nbw-wide panel (nbw <= NB) in one launch: one CTA per 64 rows, no recursion
+int trsm_panel_launch(gpp_handle* h, double* P, long ldp, const TrsmRows& rm, const double* L, long ldl, int nbw);
 int fill_identity_launch(gpp_handle* h, double* A, long ld, int rows, int cols);
 // X * L^T = P in place; P = rows x nb block of P at (pr0, pc0); L = nb x nb lower block of L at (lr0, lc0)
 int trsm_right_lt(gpp_handle* h, const Mat& P, int pr0, int pc0, int rows, const Mat& L, int lr0, int lc0, int nb);
