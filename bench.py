@@ -290,7 +290,9 @@ def main():
     if dist is not None:
         prob.shard(dist, Q=a.Q or None)
         info = eng.dist_info()
-        grid = f"sharded, one problem over {world} GPUs, {info['P']} x {info['Q']} block-cyclic owner-computes, NCCL panel gathers"
+        how = ("finished panels stored straight into the peers' replicated buffers over NVLink by the solve kernels (CUDA IPC) + flags"
+               if eng.dist_exchange_mode() == "p2p" else "NCCL panel gathers")
+        grid = f"sharded, one problem over {world} GPUs, {info['P']} x {info['Q']} block-cyclic owner-computes, {how}"
     Xd_host, Xb_host = prob.X_domain.copy(), prob.X_boundary.copy()
     truth = u_true(Xd_host[:, 0], Xd_host[:, 1])
 

@@ -117,6 +117,10 @@ int gpp_dist_init_virtual(gpp_handle* h, int nranks);
 /* process grid, P * Q = number of ranks; block (bi, bc) belongs to rank (bi mod P) * Q + (bc mod Q) */
 int gpp_dist_set_grid(gpp_handle* h, int P, int Q);
 int gpp_dist_info(gpp_handle* h, int* rank, int* world, int* P, int* Q);
+/* how finished panels travel: 1 = peer-to-peer (the solve kernels store every finished tile straight into the peers'
+ * replicated buffers over NVLink through CUDA IPC mappings and announce it by flags), 0 = NCCL all-gather / broadcast
+ * (GPP_DIST_P2P=0, or CUDA IPC unavailable) */
+int gpp_dist_exchange_mode(gpp_handle* h);
 int gpp_dist_finalize(gpp_handle* h);
 /* sharded Gram_matrix_assembly into slot 0: this rank's block rows (bi mod P == p), no exchange */
 int gpp_dist_gram_assemble(gpp_handle* h, int layout, int kernel, const double* kparams);

@@ -61,6 +61,7 @@ def _sig(lib):
         "gpp_dist_init_virtual": [H, C.c_int],
         "gpp_dist_set_grid": [H, C.c_int, C.c_int],
         "gpp_dist_info": [H, _ip, _ip, _ip, _ip],
+        "gpp_dist_exchange_mode": [H],
         "gpp_dist_finalize": [H],
         "gpp_dist_gram_assemble": [H, C.c_int, C.c_int, _dp],
         "gpp_dist_get_diag": [H, _dp],
@@ -333,6 +334,10 @@ class Engine:
         v = [C.c_int() for _ in range(4)]
         self._ck(self._lib.gpp_dist_info(self._h, *[C.byref(x) for x in v]), "gpp_dist_info")
         return dict(zip(("rank", "world", "P", "Q"), (x.value for x in v)))
+
+    def dist_exchange_mode(self):
+        """'p2p' (fused peer stores over NVLink + flags) or 'nccl' (all-gather / broadcast)."""
+        return "p2p" if self._lib.gpp_dist_exchange_mode(self._h) == 1 else "nccl"
 
     def dist_finalize(self):
         self._ck(self._lib.gpp_dist_finalize(self._h), "gpp_dist_finalize")

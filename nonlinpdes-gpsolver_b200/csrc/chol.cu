@@ -373,7 +373,8 @@ constexpr int TILED_SMEM = (2 * TT * TPAD + TT * LDS_PAD + TT + 8) * 8;
 // Per entry the updates are applied one by one in column order (the rounding model of the recursive path).
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256, 1)
-trsm_panel_kernel(double* __restrict__ P, long ldp, const TrsmRows rm, const double* __restrict__ L, long ldl, int nbw) {
+trsm_panel_kernel(double* __restrict__ P, long ldp, const TrsmRows rm, const double* __restrict__ L, long ldl, int nbw,
+                  const __grid_constant__ PeerPush pp) {
   extern __shared__ double tsm[];
   double* sAt = tsm;                       // [TT][TPAD] X tile (k-major) / transposed diagonal factor
   double* sBt = tsm + TT * TPAD;           // [TT][TPAD] L[cb, c] tile (k-major)
@@ -435,9 +436,28 @@ trsm_panel_kernel(double* __restrict__ P, long ldp, const TrsmRows rm, const dou
     __syncthreads();
     for (int e = tid; e < TT * TT; e += 256) {
       const int r = e / TT, c = e % TT;
-      if (r < nrow && c < wcb) Pt[(long)r * ldp + c0 + c] = st[r * LDS_PAD + c];
+      if (r < nrow && c < wcb) {
+        const double v = st[r * LDS_PAD + c];
+        const long off = (long)r * ldp + c0 + c;
+        Pt[off] = v;
+        for (int q = 0; q < pp.npeers; ++q) pp.base[q][prow0 * ldp + off] = v;     // the gather, fused: NVLink stores
+      }
     }
     __syncthreads();      // the solved tile is read back (as X[:, cb]) by other threads of this CTA in the next sweep
+  }
+  if (pp.npeers > 0) {
+    // all peer stores of this CTA before its arrival; the last CTA publishes the flags
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned prev = atomicAdd(pp.counter, 1u);
+      if (prev == gridDim.x - 1) {
+        atomicExch(pp.counter, 0u);
+        __threadfence_system();
+        for (int q = 0; q < pp.npeers; ++q)
+          asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(pp.flag[q]), "l"(pp.seq) : "memory");
+      }
+    }
   }
 }
 constexpr int PANEL_SMEM = (2 * TT * TPAD + TT * LDS_PAD) * 8;
@@ -634,15 +654,17 @@ int trsm_base_launch(gpp_handle* h, double* P, long ldp, const TrsmRows& rm, con
   return GPP_OK;
 }
 
-int trsm_panel_launch(gpp_handle* h, double* P, long ldp, const TrsmRows& rm, const double* L, long ldl, int nbw) {
+int trsm_panel_launch(gpp_handle* h, double* P, long ldp, const TrsmRows& rm, const double* L, long ldl, int nbw, const PeerPush* push) {
   if (rm.rows <= 0 || nbw <= 0) return GPP_OK;
+  PeerPush pp{};
+  if (push) pp = *push;
   if (rm.stride_blk != 0 && rm.nb % TT) { h->err = "trsm_panel: cyclic block size must be a multiple of 64"; return -1; }
   static bool attr[64] = {false};
   if (h->device >= 64 || !attr[h->device]) {
     CUDA_TRY(h, cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM));
     if (h->device < 64) attr[h->device] = true;
   }
-  trsm_panel_kernel<<<(rm.rows + TT - 1) / TT, 256, PANEL_SMEM, h->cur>>>(P, ldp, rm, L, ldl, nbw);
+  trsm_panel_kernel<<<(rm.rows + TT - 1) / TT, 256, PANEL_SMEM, h->cur>>>(P, ldp, rm, L, ldl, nbw, pp);
   h->launches++;
   CUDA_TRY(h, cudaGetLastError());
   return GPP_OK;

@@ -78,6 +78,15 @@ struct DistState {
   cudaStream_t sC = nullptr;     // communication stream of the U phase
   std::map<int, Plan> plans;     // key: phase * 4096 + virtual rank
   bool inverse_ready = false;
+  // peer-to-peer path (default for world > 1): the replicated buffers of all ranks are mapped into every process
+  // (CUDA IPC); finished blocks are stored straight into the peers' copies over NVLink and announced by flags
+  bool p2p = true;
+  struct PeerMap { size_t cap = 0; double* peer[8] = {nullptr}; } pm[3];   // 0: Theta / L, 1: U, 2: H
+  unsigned long long* flags = nullptr;          // [2][8] on this device: [kind][source rank], kind 0 panel, 1 diagonal block
+  unsigned long long* peer_flags[8] = {nullptr};
+  unsigned* push_counter = nullptr;             // [4]
+  unsigned char* ipc_dev = nullptr;             // staging of the handle exchange
+  unsigned long long seq = 0;                   // push sequence number, identical on all ranks
 };
 
 DistState* ds(gpp_handle* h) { return static_cast<DistState*>(h->dist); }
@@ -164,6 +173,51 @@ panel_copy_kernel(double* __restrict__ X, long ld, double* __restrict__ buf, con
       else xr[c] = br[c];
     }
   }
+}
+
+// ---- peer-to-peer push: copy a w-wide column strip of own rows (contiguous or block-cyclic) to the same place of every
+// peer's buffer, then announce it.  grid.x CTAs, each warp a row at a time.
+__global__ void __launch_bounds__(256)
+push_rows_kernel(const double* __restrict__ X, long ld, const TrsmRows rm, int w, const __grid_constant__ PeerPush pp) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = blockIdx.x * 8 + warp; r < rm.rows; r += gridDim.x * 8) {
+    const long pr = rm.stride_blk == 0 ? r : (long)(rm.first_blk + (r / rm.nb) * rm.stride_blk) * rm.nb + r % rm.nb;
+    const double* src = X + pr * ld;
+    for (int c = lane; c < w; c += 32) {
+      const double v = src[c];
+      for (int q = 0; q < pp.npeers; ++q) pp.base[q][pr * ld + c] = v;
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(pp.counter, 1u);
+    if (prev == gridDim.x - 1) {
+      atomicExch(pp.counter, 0u);
+      __threadfence_system();
+      for (int q = 0; q < pp.npeers; ++q)
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(pp.flag[q]), "l"(pp.seq) : "memory");
+    }
+  }
+}
+// nothing to push at this step: only the announcement
+__global__ void signal_kernel(const __grid_constant__ PeerPush pp) {
+  if (threadIdx.x < pp.npeers) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(pp.flag[threadIdx.x]), "l"(pp.seq) : "memory");
+  }
+}
+// wait until the flags of the sources in `mask` have reached seq (written by the peers' push kernels)
+__global__ void wait_flags_kernel(const unsigned long long* __restrict__ flags, unsigned mask, unsigned long long seq) {
+  const int r = threadIdx.x;
+  if (r < 8 && ((mask >> r) & 1u)) {
+    unsigned long long v;
+    do {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + r) : "memory");
+    } while (v < seq);
+  }
+  __syncthreads();
+  __threadfence_system();
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -420,10 +474,120 @@ int ensure_staging(gpp_handle* h, DistState* d, int n, int NB) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// peer-to-peer plumbing
+// ---------------------------------------------------------------------------------------------------------
+// exchange the CUDA IPC handle of `base` (an allocation start) with all ranks and map the peers' allocations
+int ipc_exchange(gpp_handle* h, DistState* d, void* base, void** peer_out) {
+  cudaIpcMemHandle_t mine;
+  CUDA_TRY(h, cudaIpcGetMemHandle(&mine, base));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+  if (!d->ipc_dev) CUDA_TRY(h, cudaMalloc(&d->ipc_dev, 8 * 64));
+  cudaStream_t S = h->stream;
+  CUDA_TRY(h, cudaMemcpyAsync(d->ipc_dev + 64 * d->rank, &mine, 64, cudaMemcpyHostToDevice, S));
+  NCCL_TRY(h, ncclAllGather(d->ipc_dev + 64 * d->rank, d->ipc_dev, 64, ncclChar, d->comm, S));
+  cudaIpcMemHandle_t all[8];
+  CUDA_TRY(h, cudaMemcpyAsync(all, d->ipc_dev, 64 * d->world, cudaMemcpyDeviceToHost, S));
+  CUDA_TRY(h, cudaStreamSynchronize(S));
+  for (int r = 0; r < d->world; ++r) {
+    if (r == d->rank) { peer_out[r] = base; continue; }
+    CUDA_TRY(h, cudaIpcOpenMemHandle(&peer_out[r], all[r], cudaIpcMemLazyEnablePeerAccess));
+  }
+  return GPP_OK;
+}
+
+bool use_p2p(const DistState* d) { return d->p2p && d->world > 1 && d->world <= 8 && d->nv == 0; }
+
+// (re)map replicated buffer `which` after it was (re)allocated; `cap` is its capacity, which changes on every rank at
+// the same call (identical sizes), so the exchange stays collective
+int share_buffer(gpp_handle* h, DistState* d, int which, double* base, size_t cap) {
+  if (!use_p2p(d)) return GPP_OK;
+  DistState::PeerMap& pm = d->pm[which];
+  if (pm.cap == cap && pm.peer[d->rank] == base) return GPP_OK;
+  for (int r = 0; r < d->world; ++r) {
+    if (r != d->rank && pm.peer[r]) cudaIpcCloseMemHandle(pm.peer[r]);
+    pm.peer[r] = nullptr;
+  }
+  void* peers[8] = {nullptr};
+  int rc = ipc_exchange(h, d, base, peers);
+  if (rc) return rc;
+  for (int r = 0; r < d->world; ++r) pm.peer[r] = static_cast<double*>(peers[r]);
+  pm.cap = cap;
+  return GPP_OK;
+}
+
+int init_p2p(gpp_handle* h, DistState* d) {
+  if (!use_p2p(d)) return GPP_OK;
+  CUDA_TRY(h, cudaMalloc(&d->flags, 16 * sizeof(unsigned long long)));
+  CUDA_TRY(h, cudaMemset(d->flags, 0, 16 * sizeof(unsigned long long)));
+  CUDA_TRY(h, cudaMalloc(&d->push_counter, 4 * sizeof(unsigned)));
+  CUDA_TRY(h, cudaMemset(d->push_counter, 0, 4 * sizeof(unsigned)));
+  void* peers[8] = {nullptr};
+  int rc = ipc_exchange(h, d, d->flags, peers);
+  if (rc) return rc;
+  for (int r = 0; r < d->world; ++r) d->peer_flags[r] = static_cast<unsigned long long*>(peers[r]);
+  return GPP_OK;
+}
+
+// push descriptor for a kernel whose output origin is `local_ptr` inside replicated buffer `which`
+PeerPush make_push(DistState* d, int which, const double* local_ptr, int kind, unsigned long long seq) {
+  PeerPush pp{};
+  const DistState::PeerMap& pm = d->pm[which];
+  const long off = local_ptr - pm.peer[d->rank];
+  for (int r = 0; r < d->world; ++r) {
+    if (r == d->rank) continue;
+    pp.base[pp.npeers] = pm.peer[r] + off;
+    pp.flag[pp.npeers] = d->peer_flags[r] + kind * 8 + d->rank;
+    ++pp.npeers;
+  }
+  pp.seq = seq;
+  pp.counter = d->push_counter + kind;
+  return pp;
+}
+
+int push_rows(gpp_handle* h, const double* X, long ld, const TrsmRows& rm, int w, const PeerPush& pp, cudaStream_t st) {
+  if (rm.rows <= 0 || w <= 0) {
+    signal_kernel<<<1, 32, 0, st>>>(pp);
+  } else {
+    int grid = (rm.rows + 7) / 8;
+    if (grid > 296) grid = 296;
+    push_rows_kernel<<<grid, 256, 0, st>>>(X, ld, rm, w, pp);
+  }
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return GPP_OK;
+}
+
+int wait_flags(gpp_handle* h, DistState* d, int kind, int root, unsigned long long seq, cudaStream_t st) {
+  unsigned mask = 0;
+  for (int r = 0; r < d->world; ++r)
+    if (r != d->rank && (root < 0 || r == root)) mask |= 1u << r;
+  if (!mask) return GPP_OK;
+  wait_flags_kernel<<<1, 32, 0, st>>>(d->flags + kind * 8, mask, seq);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return GPP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // distributed right-looking Cholesky of the replicated n x n matrix A (Theta in slot 0, or the GN Hessian)
 // ---------------------------------------------------------------------------------------------------------
-int dist_potrf_matrix(gpp_handle* h, DistState* d, double* A, long ld, int n, const TMap2* map, int phase, bool want_info, int* info) {
+// all ranks have finished whatever they enqueued before: one-sided pushes into their buffers may start
+int phase_barrier(gpp_handle* h, DistState* d) {
+  if (!use_p2p(d)) return GPP_OK;
+  NCCL_TRY(h, ncclAllReduce(d->push_counter + 3, d->push_counter + 3, 1, ncclUint32, ncclSum, d->comm, h->stream));
+  return GPP_OK;
+}
+
+int dist_potrf_matrix(gpp_handle* h, DistState* d, double* A, long ld, int n, const TMap2* map, int phase, bool want_info, int* info,
+                      size_t cap) {
   const int NB = h->NB;
+  const int which = (phase == 3) ? 2 : 0;
+  const bool p2p = use_p2p(d);
+  if (p2p) {
+    int rcs = share_buffer(h, d, which, A, cap);
+    if (!rcs) rcs = phase_barrier(h, d);
+    if (rcs) return rcs;
+  }
   const int nblk = nblocks_of(n, NB);
   const MatRef Am{A, ld, map};
   const std::vector<Grid> grids = grids_of(d);
@@ -485,11 +649,46 @@ int dist_potrf_matrix(gpp_handle* h, DistState* d, double* A, long ld, int n, co
       tmark(cur_chain, 1);
       int r = panel_factor(g, j);
       tmark(cur_chain, 2);
-      if (!r) r = bcast_diag(h, d, A, ld, n, NB, j, Sp);
+      const int j0 = j * NB, w = rows_of(n, NB, j);
+      double* diag = A + (long)j0 * ld + j0;
+      if (!p2p) {
+        if (!r) r = bcast_diag(h, d, A, ld, n, NB, j, Sp);
+        tmark(cur_chain, 3);
+        if (!r) r = panel_solve(pl, j);
+        tmark(cur_chain, 4);
+        if (!r) r = gather_panel(h, d, A, ld, n, NB, j, j + 1, nblk, Sp);
+        tmark(cur_chain, 5);
+        return r;
+      }
+      // peer-to-peer: the owner stores the factored diagonal block into every peer's copy; the panel solve stores each
+      // solved tile into every peer's copy as it goes (the gather is part of the kernel); flags announce completion
+      const int root = owner_of(g, j, j);
+      const unsigned long long sd = ++d->seq;
+      if (!r) {
+        if (d->rank == root) {
+          const TrsmRows dr{w, 0, 0, 0};
+          r = push_rows(h, diag, ld, dr, w, make_push(d, which, diag, 1, sd), Sp);
+        } else {
+          r = wait_flags(h, d, 1, root, sd, Sp);
+        }
+      }
       tmark(cur_chain, 3);
-      if (!r) r = panel_solve(pl, j);
-      tmark(cur_chain, 4);
-      if (!r) r = gather_panel(h, d, A, ld, n, NB, j, j + 1, nblk, Sp);
+      if (j + 1 < nblk && !r) {
+        const unsigned long long sp = ++d->seq;
+        const TrsmRows& rm = pl.rows[j];
+        double* Pcol = A + j0;
+        const PeerPush pp = make_push(d, which, Pcol, 0, sp);
+        if (rm.rows > 0 && rm.rows <= h->fused_trsm_rows) {
+          r = trsm_panel_launch(h, Pcol, ld, rm, diag, ld, w, &pp);
+        } else {
+          if (rm.rows > 0) r = panel_solve(pl, j);
+          if (!r) r = push_rows(h, Pcol, ld, rm, w, pp, Sp);
+        }
+        tmark(cur_chain, 4);
+        if (!r) r = wait_flags(h, d, 0, -1, sp, Sp);
+      } else {
+        tmark(cur_chain, 4);
+      }
       tmark(cur_chain, 5);
       return r;
     };
@@ -561,17 +760,43 @@ int dist_uinv(gpp_handle* h, DistState* d, GramSlot& s) {
   int rc = ensure_staging(h, d, n, NB);
   if (rc) return rc;
   cudaStream_t S = h->stream;
+  const bool p2p = use_p2p(d);
+  if (p2p) {
+    rc = share_buffer(h, d, 1, d->U, h->caps.count(&d->U) ? h->caps[&d->U] : 0);
+    if (!rc) rc = phase_barrier(h, d);
+    if (rc) return rc;
+  }
   CUDA_TRY(h, cudaMemsetAsync(d->U, 0, sizeof(double) * (size_t)n * s.ld, S));
+  if (p2p) {
+    // nobody may push into this rank's U before its memset has run: second barrier, after the memset
+    rc = phase_barrier(h, d);
+    if (rc) return rc;
+  }
+  unsigned long long last_seq = 0;
 
   auto panel_solve = [&](const Grid& g, const Plan& pl, int i) -> int {     // on h->cur
     const int i0 = i * NB, nbi = rows_of(n, NB, i);
     int r = GPP_OK;
     if (owner_of(g, i, i) == g.p * g.Q + g.q) r = fill_identity_launch(h, d->U + (long)i0 * s.ld + i0, s.ld, nbi, nbi);
     if (r) return r;
-    if (pl.rows[i].rows <= h->fused_trsm_rows)
-      return trsm_panel_launch(h, d->U + i0, s.ld, pl.rows[i], s.T + (long)i0 * s.ld + i0, s.ld, nbi);
+    const TrsmRows& rm = pl.rows[i];
+    if (p2p) {
+      // every finished column of U goes straight into the peers' copies (all of U is needed by every rank afterwards)
+      last_seq = ++d->seq;
+      const PeerPush pp = make_push(d, 1, d->U + i0, 0, last_seq);
+      if (rm.rows > 0 && rm.rows <= h->fused_trsm_rows)
+        return trsm_panel_launch(h, d->U + i0, s.ld, rm, s.T + (long)i0 * s.ld + i0, s.ld, nbi, &pp);
+      if (rm.rows > 0) {
+        size_t next = 0;
+        r = exec_trsm(h, pl, pl.trsm[i], next, rm, Um, i0, Tm, i0, i0, nbi, NB);
+        if (r) return r;
+      }
+      return push_rows(h, d->U + i0, s.ld, rm, nbi, pp, h->cur);
+    }
+    if (rm.rows <= h->fused_trsm_rows)
+      return trsm_panel_launch(h, d->U + i0, s.ld, rm, s.T + (long)i0 * s.ld + i0, s.ld, nbi);
     size_t next = 0;
-    return exec_trsm(h, pl, pl.trsm[i], next, pl.rows[i], Um, i0, Tm, i0, i0, nbi, NB);
+    return exec_trsm(h, pl, pl.trsm[i], next, rm, Um, i0, Tm, i0, i0, nbi, NB);
   };
 
   if (d->nv > 0) {
@@ -601,7 +826,12 @@ int dist_uinv(gpp_handle* h, DistState* d, GramSlot& s) {
     h->cur = Sp;
     int r = panel_solve(g, pl, i);
     if (r) return r;
-    if (d->Q > 1) {
+    if (p2p) {
+      // Q > 1: the other process columns need U(b, i) for their updates, wait for the pushes; Q = 1: own rows only
+      if (d->Q > 1) r = wait_flags(h, d, 0, -1, last_seq, Sp);
+      ev_panel[i] = ev.get();
+      CUDA_TRY(h, cudaEventRecord(ev_panel[i], Sp));
+    } else if (d->Q > 1) {
       // the other process columns need U(b, i) for their updates: gather on the critical path
       r = gather_panel(h, d, d->U, s.ld, n, NB, i, 0, i + 1, Sp);
       ev_panel[i] = ev.get();
@@ -645,6 +875,7 @@ int dist_uinv(gpp_handle* h, DistState* d, GramSlot& s) {
   CUDA_TRY(h, cudaStreamWaitEvent(S, e1, 0));
   CUDA_TRY(h, cudaStreamWaitEvent(S, e2, 0));
   CUDA_TRY(h, cudaStreamWaitEvent(S, e3, 0));
+  if (p2p && last_seq) return wait_flags(h, d, 0, -1, last_seq, S);      // every peer's last column has landed: U is complete here
   return GPP_OK;
 }
 
@@ -693,7 +924,7 @@ int dist_gn_hess_potrf(gpp_handle* h) {
     if (rc) return rc;
     base_blocks += pl.hblocks.size();
   }
-  return dist_potrf_matrix(h, d, g.H, g.ldH, g.n, &g.mapH, 3, false, nullptr);
+  return dist_potrf_matrix(h, d, g.H, g.ldH, g.n, &g.mapH, 3, false, nullptr, h->caps.count(&g.H) ? h->caps[&g.H] : 0);
 }
 
 extern "C" {
@@ -728,7 +959,28 @@ int gpp_dist_init(gpp_handle* h, int rank, int world, const unsigned char* id128
   memcpy(&id, id128, 128);
   ncclResult_t r = ncclCommInitRank(&d->comm, world, id, rank);
   if (r != ncclSuccess) { h->err = std::string("ncclCommInitRank: ") + ncclGetErrorString(r); delete d; return GPP_CUDA_ERR + 2; }
-  return dist_common_init(h, d);
+  const char* env = getenv("GPP_DIST_P2P");
+  if (env && env[0] == '0') d->p2p = false;
+  int rc = dist_common_init(h, d);
+  if (rc) return rc;
+  if (use_p2p(d)) {
+    // CUDA IPC may be unavailable (container restrictions): agree among all ranks, otherwise use the NCCL gathers
+    int ok = init_p2p(h, d) == GPP_OK ? 1 : 0;
+    int* d_ok = nullptr;
+    CUDA_TRY(h, cudaMalloc(&d_ok, sizeof(int)));
+    CUDA_TRY(h, cudaMemcpy(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice));
+    NCCL_TRY(h, ncclAllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, d->comm, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    CUDA_TRY(h, cudaMemcpy(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost));
+    cudaFree(d_ok);
+    if (!ok) {
+      if (getenv("GPP_TRACE")) fprintf(stderr, "[gpp trace] rank %d: CUDA IPC not available (%s): NCCL gathers\n", rank, h->err.c_str());
+      d->p2p = false;
+      cudaGetLastError();
+      h->err.clear();
+    }
+  }
+  return GPP_OK;
 }
 
 int gpp_dist_init_virtual(gpp_handle* h, int nranks) {
@@ -761,13 +1013,31 @@ int gpp_dist_info(gpp_handle* h, int* rank, int* world, int* P, int* Q) {
   return GPP_OK;
 }
 
+int gpp_dist_exchange_mode(gpp_handle* h) {
+  if (!h || !h->dist) return -1;
+  return use_p2p(ds(h)) ? 1 : 0;
+}
+
 int gpp_dist_finalize(gpp_handle* h) {
   if (h) cudaSetDevice(h->device);
   if (!h || !h->dist) return -1;
   DistState* d = ds(h);
   cudaStreamSynchronize(h->stream);
   cudaDeviceSynchronize();
-  if (d->comm) ncclCommDestroy(d->comm);
+  for (auto& pm : d->pm)
+    for (int r = 0; r < d->world; ++r)
+      if (r != d->rank && pm.peer[r]) cudaIpcCloseMemHandle(pm.peer[r]);
+  for (int r = 0; r < d->world; ++r)
+    if (r != d->rank && d->peer_flags[r]) cudaIpcCloseMemHandle(d->peer_flags[r]);
+  if (d->comm) {
+    // the peers may still have this rank's buffers mapped: leave together
+    if (d->world > 1 && d->push_counter) ncclAllReduce(d->push_counter + 3, d->push_counter + 3, 1, ncclUint32, ncclSum, d->comm, h->stream);
+    cudaStreamSynchronize(h->stream);
+    ncclCommDestroy(d->comm);
+  }
+  if (d->flags) cudaFree(d->flags);
+  if (d->push_counter) cudaFree(d->push_counter);
+  if (d->ipc_dev) cudaFree(d->ipc_dev);
   dev_release(h, &d->U); dev_release(h, &d->Asub); dev_release(h, &d->gbuf); dev_release(h, &d->dbuf); dev_release(h, &d->dvec);
   for (auto& kv : d->plans) {
     if (kv.second.dev) cudaFree(kv.second.dev);
@@ -868,7 +1138,7 @@ int gpp_dist_potrf(gpp_handle* h, int* info) {
   if (!s.T) { h->err = "assemble first"; return -2; }
   if (s.factored) { h->err = "already factored"; return -3; }
   CUDA_TRY(h, cudaSetDevice(h->device));
-  int rc = dist_potrf_matrix(h, d, s.T, s.ld, s.M, &s.mapT, 0, true, info);
+  int rc = dist_potrf_matrix(h, d, s.T, s.ld, s.M, &s.mapT, 0, true, info, h->caps.count(&s.T) ? h->caps[&s.T] : 0);
   if (rc) return rc;
   s.factored = true;
   s.inverted = false;

@@ -218,10 +218,21 @@ struct TrsmRows {
   int rows;
   int first_blk, stride_blk, nb;
 };
+// Peer push (multi-GPU, replicated storage): results are stored not only locally but at the same position of every
+// peer's buffer through NVLink (CUDA IPC mappings), and when the whole launch is done each peer's flag slot of this
+// rank is set to `seq` (release at system scope).  npeers == 0: local only.
+#define GPP_MAX_PEERS 7
+struct PeerPush {
+  int npeers;
+  double* base[GPP_MAX_PEERS];                // peer copy of the pointer the kernel receives as its output origin
+  unsigned long long* flag[GPP_MAX_PEERS];    // peer's flag slot for this rank
+  unsigned long long seq;
+  unsigned* counter;                          // local CTA counter (self-resetting)
+};
 // 64-wide base case of the panel solve X L^T = P (in place), L = nbl x nbl lower block; P points at column 0 of the panel
 int trsm_base_launch(gpp_handle* h, double* P, long ldp, const TrsmRows& rm, const double* L, long ldl, int nbl);
 // the same solve for the whole nbw-wide panel (nbw <= NB) in one launch: one CTA per 64 rows, no recursion
-int trsm_panel_launch(gpp_handle* h, double* P, long ldp, const TrsmRows& rm, const double* L, long ldl, int nbw);
+int trsm_panel_launch(gpp_handle* h, double* P, long ldp, const TrsmRows& rm, const double* L, long ldl, int nbw, const PeerPush* push = nullptr);
 int fill_identity_launch(gpp_handle* h, double* A, long ld, int rows, int cols);
 // X * L^T = P in place; P = rows x nb block of P at (pr0, pc0); L = nb x nb lower block of L at (lr0, lc0)
 int trsm_right_lt(gpp_handle* h, const Mat& P, int pr0, int pc0, int rows, const Mat& L, int lr0, int lc0, int nb);

@@ -76,7 +76,7 @@ for rep in range(a.reps):
     asm, potrf, inv, gn, tot = maxred([t["assembly_ms"], t["potrf_ms"], t["inverse_ms"], t["gn_ms"], total])
     err = np.abs(u_true(prob.X_domain[:, 0], prob.X_domain[:, 1]) - prob.sol_sampled_pts)
     if rank == 0:
-        print(json.dumps(dict(world=a.virtual or world, virtual=bool(a.virtual), grid=eng.dist_info(), N=N, M=M, NB=a.NB, rep=rep, info=prob.chol_info,
+        print(json.dumps(dict(world=a.virtual or world, virtual=bool(a.virtual), grid=eng.dist_info(), exchange=eng.dist_exchange_mode(), N=N, M=M, NB=a.NB, rep=rep, info=prob.chol_info,
                               asm_ms=round(asm, 3), potrf_ms=round(potrf, 2), potrf_TF=round(M ** 3 / 3 / potrf / 1e9, 2),
                               inverse_ms=round(inv, 2), inverse_TF=round(2 * M ** 3 / 3 / inv / 1e9, 2), gn_ms=round(gn, 2),
                               gn_step_ms=round(gn / a.gn_steps, 2), solve_ms=round(tot, 2), final_loss=prob.loss_hist[-1],
