@@ -152,11 +152,12 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target) {
 // of potrf_base_kernel (updates applied one by one in column order).
 __device__ __forceinline__ void tile_potrf_smem(double* st, double* col, double* sdiag, int nb, int gidx0, int* info) {
   const int i = threadIdx.x;
+  if (i < TT) {
+    // only the two warps that own the 64 rows synchronise inside (named barrier 1); the rest of the CTA waits below
 #pragma unroll 1
-  for (int pass = 0; pass < 2; ++pass) {
-    const int c0 = 32 * pass;
-    double a[32];
-    if (i < TT) {
+    for (int pass = 0; pass < 2; ++pass) {
+      const int c0 = 32 * pass;
+      double a[32];
 #pragma unroll
       for (int k = 0; k < 32; ++k) a[k] = (i < nb && c0 + k <= i) ? st[i * LDS_PAD + c0 + k] : (c0 + k == i ? 1.0 : 0.0);
       if (pass == 1) {
@@ -168,35 +169,30 @@ __device__ __forceinline__ void tile_potrf_smem(double* st, double* col, double*
           for (int k = 0; k < 32; ++k) a[k] = fma(-lij, st[(32 + k) * LDS_PAD + j], a[k]);
         }
       }
-    }
 #pragma unroll
-    for (int jj = 0; jj < 32; ++jj) {
-      const int j = c0 + jj;
-      if (i == j) {
-        const double d = a[jj];
-        if (!(d > 0.0) && j < nb) atomicCAS(info, 0, gidx0 + j + 1);
-        const double sq = sqrt(d);
-        a[jj] = sq;
-        *sdiag = sq;
-      }
-      __syncthreads();
-      double l = 0.0;
-      if (i < TT) {
+      for (int jj = 0; jj < 32; ++jj) {
+        const int j = c0 + jj;
+        if (i == j) {
+          const double d = a[jj];
+          if (!(d > 0.0) && j < nb) atomicCAS(info, 0, gidx0 + j + 1);
+          const double sq = sqrt(d);
+          a[jj] = sq;
+          *sdiag = sq;
+        }
+        asm volatile("bar.sync 1, 64;" ::: "memory");
+        double l = 0.0;
         if (i > j) { l = a[jj] / *sdiag; a[jj] = l; }
         col[i] = l;
-      }
-      __syncthreads();
-      if (i < TT) {
+        asm volatile("bar.sync 1, 64;" ::: "memory");
 #pragma unroll
         for (int k = jj + 1; k < 32; ++k) a[k] = fma(-l, col[c0 + k], a[k]);
       }
-    }
-    if (i < TT) {
 #pragma unroll
       for (int k = 0; k < 32; ++k) st[i * LDS_PAD + c0 + k] = a[k];
+      asm volatile("bar.sync 1, 64;" ::: "memory");
     }
-    __syncthreads();
   }
+  __syncthreads();
 }
 
 // rows of st (row-major, threads 0..63 one row each) solved against the transposed factor in sLt (sLt[j * TPAD + k] =

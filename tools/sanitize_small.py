@@ -15,4 +15,10 @@ e.sampled_pts(700, 100); e.Gram_matrix("Gaussian", 0.2, 1e-5); e.Gram_Cholesky()
 d = InverseProblems.Darcy_flow2d(bdy=lambda x, y: 0, rhs=lambda x, y: 1)
 d.sampled_pts(150, 40, 20); d.get_observation(np.zeros(20), 1e-2); d.Gram_matrix("Gaussian", 0.2, 1e-6); d.Gram_Cholesky(); d.GN_method(2, 1, "rdm", print_hist=False)
 d.extend_sol(np.random.uniform(0, 1, (30, 2)))
+# the sharded path (task-list GEMM, fused panel solve, block Hessian) with 4 virtual ranks on a 2 x 2 grid
+sh = PDEs.Nonlinear_elliptic2d(alpha=1.0, m=3, bdy=lambda x, y: np.sin(x + y), rhs=lambda x, y: x * y)
+sh._engine().set_option("NB", 128)
+sh.sampled_pts(500, 60); sh.shard(virtual_ranks=4, Q=2)
+sh.Gram_matrix("Gaussian", 0.2, 1e-6); sh.Gram_Cholesky(); sh.GN_method(2, 1, "rdm", print_hist=False)
+print("sharded (virtual 2 x 2):", sh.loss_hist[-1])
 print("sanitize run finished:", p.loss_hist[-1], b.loss_hist[-1], e.loss_hist[-1], d.loss_hist[-1])
