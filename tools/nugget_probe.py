@@ -11,6 +11,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--N", type=int, nargs="+", default=[10000, 20000])
 ap.add_argument("--nuggets", type=float, nargs="+", default=[1e-13, 1e-12])
 ap.add_argument("--lapack_max", type=int, default=20000)
+ap.add_argument("--variants", action="store_true", help="also try other schedules of the device factorisation (NB, right-looking)")
 a = ap.parse_args()
 try:
     from threadpoolctl import threadpool_limits
@@ -34,6 +35,29 @@ for N in a.N:
             del th
         p.Gram_Cholesky()
         rec.update(gpu_info=int(p.chol_info), gpu_potrf_ms=round(p.timings["potrf_ms"], 1))
+        if a.variants:
+            # the same matrix through other schedules: block width (the "panel width") and the right-looking sharded
+            # schedule with one rank; near the edge the outcome depends on the rounding pattern, not on one of them being better
+            var = {}
+            for nb in (128, 256, 1024):
+                q = PDEs.Nonlinear_elliptic2d(alpha=1.0, m=3, bdy=lambda x, y: 0 * x, rhs=lambda x, y: 0 * x)
+                q._eng = p._engine()
+                q._eng.set_option("NB", nb)
+                q.get_sampled_points(p.X_domain, p.X_boundary)
+                q.Gram_matrix("Gaussian", 0.2, ng, "adaptive")
+                q.Gram_Cholesky()
+                var[f"left_looking_NB{nb}"] = int(q.chol_info)
+            p._engine().set_option("NB", 512)
+            from nonlinpdes_gpsolver_b200 import _lib
+            r = PDEs.Nonlinear_elliptic2d(alpha=1.0, m=3, bdy=lambda x, y: 0 * x, rhs=lambda x, y: 0 * x)
+            r._eng = _lib.Engine()
+            r.get_sampled_points(p.X_domain, p.X_boundary)
+            r.shard(virtual_ranks=1)
+            r.Gram_matrix("Gaussian", 0.2, ng, "adaptive")
+            r.Gram_Cholesky()
+            var["right_looking_NB512"] = int(r.chol_info)
+            r._eng.close()
+            rec["gpu_info_other_schedules"] = var
         rec["verdict"] = ("both fail: indefinite in FP64" if rec.get("lapack_dpotrf_info", 0) > 0 and rec["gpu_info"] > 0 else
                           "both succeed" if rec.get("lapack_dpotrf_info", 1) == 0 and rec["gpu_info"] == 0 else
                           "GPU succeeds, LAPACK fails" if rec["gpu_info"] == 0 else "GPU fails, LAPACK succeeds / not run")
