@@ -78,9 +78,12 @@ struct DistState {
   cudaStream_t sC = nullptr;     // communication stream of the U phase
   std::map<int, Plan> plans;     // key: phase * 4096 + virtual rank
   bool inverse_ready = false;
-  // peer-to-peer path (default for world > 1): the replicated buffers of all ranks are mapped into every process
-  // (CUDA IPC); finished blocks are stored straight into the peers' copies over NVLink and announced by flags
-  bool p2p = true;
+  // peer-to-peer path (GPP_DIST_P2P=1): the replicated buffers of all ranks are mapped into every process (CUDA IPC);
+  // finished blocks are stored straight into the peers' copies over NVLink by the solve kernel and announced by flags.
+  // Measured on 8 B200 (profiles/r02b_dist8_*.log): 3.79 s per N=40k solve against 2.98 s with the NCCL all-gather --
+  // every tile is written 7 times by the SMs of the kernel on the critical path, where NCCL's all-gather is not -- so
+  // NCCL is the default and this path is an option.
+  bool p2p = false;
   struct PeerMap { size_t cap = 0; double* peer[8] = {nullptr}; } pm[3];   // 0: Theta / L, 1: U, 2: H
   unsigned long long* flags = nullptr;          // [2][8] on this device: [kind][source rank], kind 0 panel, 1 diagonal block
   unsigned long long* peer_flags[8] = {nullptr};
@@ -960,7 +963,7 @@ int gpp_dist_init(gpp_handle* h, int rank, int world, const unsigned char* id128
   ncclResult_t r = ncclCommInitRank(&d->comm, world, id, rank);
   if (r != ncclSuccess) { h->err = std::string("ncclCommInitRank: ") + ncclGetErrorString(r); delete d; return GPP_CUDA_ERR + 2; }
   const char* env = getenv("GPP_DIST_P2P");
-  if (env && env[0] == '0') d->p2p = false;
+  if (env) d->p2p = env[0] == '1';
   int rc = dist_common_init(h, d);
   if (rc) return rc;
   if (use_p2p(d)) {

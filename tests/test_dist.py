@@ -160,16 +160,19 @@ def test_virtual_sharded_factor_failure_is_reported():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("Q", [1, 2])
-def test_sharded_solve_two_gpus_nccl(Q):
+@pytest.mark.parametrize("Q,p2p", [(1, "0"), (2, "0"), (1, "1"), (2, "1")])
+def test_sharded_solve_two_gpus(Q, p2p):
+    """The real exchange paths on 2 GPUs: NCCL all-gather / broadcast (default) and peer stores over NVLink (GPP_DIST_P2P=1)."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                           "--master-port", "29612", os.path.join(ROOT, "tools", "dist_solve.py"), "--N", "1500", "--NB", "256", "--reps", "1",
-                          "--nugget", "1e-8", "--Q", str(Q), "--check"], capture_output=True, text=True, timeout=600)
+                          "--nugget", "1e-8", "--Q", str(Q), "--check"], capture_output=True, text=True, timeout=600,
+                         env=dict(os.environ, GPP_DIST_P2P=p2p))
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert '"ok": true' in out.stdout
+    assert ('"exchange": "p2p"' if p2p == "1" else '"exchange": "nccl"') in out.stdout
 
 
 @pytest.mark.gpu
