@@ -7,8 +7,10 @@ A "step" is one pass of the hot path over one batch of synthetic input: Gram ass
 inverse -> GNsteps Gauss-Newton steps of the nonlinear elliptic problem (BASELINE configs[4]: N_domain collocation
 points, Gaussian sigma=0.2, 4 GN steps; manufactured data of main_NonLinElliptic2d.py:60-64; points from the
 reference's sampler with numpy seed 0).  NOTE: the workload runs at nugget 1e-12, not the 1e-13 of configs[0]:
-at N_domain >= 20 000 Theta + 1e-13 * diag(r) is numerically indefinite in FP64 -- LAPACK dpotrf fails on it too
-(profiles/r02_nugget_lapack_vs_gpu.jsonl) -- so 1e-12 is the smallest decade at which the factorisation exists.
+at N_domain >= 20 000 the device factorisation of Theta + 1e-13 * diag(r) breaks down (first non-positive pivot near
+35 000 at N = 20 000 -- with every block width and with the right-looking schedule -- and 47 792 at N = 40 000), while
+LAPACK dpotrf on the same N = 20 000 matrix still succeeds (profiles/r02_nugget_lapack_vs_gpu.jsonl; LAPACK cannot be run
+at N = 40 000: M^2 exceeds its 32-bit indexing).  1e-12 is the smallest decade at which the device factor exists.
 
 Every timed step goes through the public facade (solver_GP: get_sample -> solve -> collocation_pts_err) with HOST
 buffers.  `e2e` is the wall clock around the K steps (host<->device copies included); `value` is the same K steps
@@ -199,7 +201,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--N_domain", type=int, default=40000)
     ap.add_argument("--gn_steps", type=int, default=4)
-    ap.add_argument("--nugget", type=float, default=1e-12)   # see the module docstring: 1e-13 is indefinite for LAPACK too at this size
+    ap.add_argument("--nugget", type=float, default=1e-12)   # see the module docstring: the device factor does not exist at 1e-13 at this size
     ap.add_argument("--cpu_sample_N", type=int, default=4000)    # ~12 s of CPU work on a 16-thread host
     ap.add_argument("--cpu_big_N", type=int, default=10000)      # reference arm only: one measured solve, ~3 min
     ap.add_argument("--cpu_lu_percall", action="store_true")     # reference arm: redo the LU of L per call like the reference
@@ -215,7 +217,8 @@ def main():
     Nb = n_boundary_for(N)
     M, n = 2 * N + Nb, N
     workload = (f"NonLinElliptic2d scaled N_domain={N} N_boundary={Nb} Gaussian sigma=0.2 nugget={a.nugget:g} GNsteps={a.gn_steps} "
-                f"(BASELINE configs[4]; nugget 1e-12 instead of 1e-13: Theta + 1e-13 diag(r) is indefinite in FP64 at this size for LAPACK too)")
+                f"(BASELINE configs[4]; nugget 1e-12 instead of 1e-13: the device Cholesky breaks down at 1e-13 for N_domain >= 20000, "
+                f"profiles/r02_nugget_lapack_vs_gpu.jsonl)")
     metric = "Gauss-Newton steps/sec"
 
     if a.impl == "reference":
