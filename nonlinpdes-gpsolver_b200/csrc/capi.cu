@@ -161,6 +161,7 @@ int gpp_set_option(gpp_handle* h, const char* name, double value) {
   if (!strcmp(name, "tiled_potrf")) { h->tiled_potrf = value != 0.0; return GPP_OK; }
   if (!strcmp(name, "tiled_max_n")) { h->tiled_max_n = (int)value; return GPP_OK; }
   if (!strcmp(name, "tiled_grid_limit")) { h->tiled_grid_limit = (int)value; return GPP_OK; }
+  if (!strcmp(name, "blocksum")) { h->blocksum = value != 0.0; return GPP_OK; }
   if (!strcmp(name, "fused_trsm_rows")) { h->fused_trsm_rows = (int)value; return GPP_OK; }
   if (!strcmp(name, "gemm_tile")) {
     const int t = (int)value;

@@ -396,6 +396,7 @@ int run_tasks(gpp_handle* h, const Plan& pl, const Launch& l, const MatRef& A, c
   d.Cin = accumulate ? C.base : nullptr; d.ldcin = C.ld;
   d.alpha = alpha;
   d.tasks = pl.dev + l.off; d.ntasks = l.count; d.bs = bs;
+  d.blocksum = (accumulate && h->blocksum) ? 1 : 0;
   return gemm_tasks_launch(h, d);
 }
 

@@ -49,6 +49,7 @@ struct GemmParams {
   // task-list mode (multi-GPU path): blockIdx.x / (task_tps^2) indexes tasks[]; see GemmTask in gpp_internal.cuh
   const GemmTask* tasks;
   int task_tps;
+  int blocksum;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -203,7 +204,7 @@ gemm_nt_dmma_kernel(const __grid_constant__ GemmParams p) {
   // value is the remainder Cin - sum_k a b (same order as a right-looking update).  For the nearly singular
   // Gram matrices of this solver the remainder shrinks quickly with k, and rounding each partial result
   // relative to the remainder -- not to the partial sum -- is what keeps pivots of size ~nugget positive.
-  const bool progressive = (Cinp != nullptr) && (p.alpha == 1.0 || p.alpha == -1.0);
+  const bool progressive = (Cinp != nullptr) && (p.alpha == 1.0 || p.alpha == -1.0) && !p.blocksum;
   if (progressive) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -348,7 +349,7 @@ int gemm_nt_launch(gpp_handle* h, const GemmDesc& d) {
   p.diag_nb = d.diag_nb > 0 ? d.diag_nb : (1 << 30);
   p.alpha = d.alpha; p.lower_only = d.lower_only;
   p.bd_mode = d.bd_count > 0; p.bd_world = d.bd_world; p.bd_rank = d.bd_rank; p.bd_lblk0 = d.bd_lblk0; p.bd_nb = d.bd_nb; p.bd_M = d.bd_M;
-  p.tasks = nullptr; p.task_tps = 0;
+  p.tasks = nullptr; p.task_tps = 0; p.blocksum = 0;
   // tile choice: 64 x 64 when the 128-tiling would occupy less than half of the SMs
   long t128;
   if (p.bd_mode) { const int nt = d.bd_nb / 128; t128 = (long)d.bd_count * (nt * (nt + 1) / 2); }
@@ -387,6 +388,7 @@ int gemm_tasks_launch(gpp_handle* h, const GemmTaskDesc& d) {
   p.diag_nb = 1 << 30;
   p.alpha = d.alpha;
   p.tasks = d.tasks;
+  p.blocksum = d.blocksum;
   p.tiles_m = p.tiles_n = 1;     // unused in task mode (kept non-zero: the generic tile decode still runs)
   const long t128 = (long)d.ntasks * (d.bs / 128) * (d.bs / 128);
   const int force = h->force_tile;

@@ -115,6 +115,8 @@ struct gpp_handle {
   int tiled_potrf = 1;        // use the persistent tiled kernel for diagonal blocks and small matrices
   int tiled_max_n = 4608;     // largest matrix factored whole by the tiled kernel
   int tiled_grid_limit = 0;   // tests / tuning: cap on its grid size (0 = resident capacity)
+  int blocksum = 0;           // task-list updates: 1 = sum the K = NB products of a launch from zero, then subtract once
+                              // (LAPACK-style block summation) instead of the entry-by-entry progressive order
   int fused_trsm_rows = 65536; // sharded path: panels with at most this many own rows use the one-launch panel solve
   double* work = nullptr;     // scratch (panel copies)
   size_t work_bytes = 0;
@@ -202,6 +204,7 @@ struct GemmTaskDesc {
   double alpha;
   const GemmTask* tasks;            // device pointer
   int ntasks, bs;                   // bs: task block size, a multiple of 128
+  int blocksum;                     // 1: accumulate the products from zero, add Cin in the epilogue
 };
 int gemm_tasks_launch(gpp_handle* h, const GemmTaskDesc& d);
 int make_tensor_map(gpp_handle* h, TMap2* map, const double* base, long rows, long cols, long ld);

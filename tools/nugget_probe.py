@@ -53,9 +53,15 @@ for N in a.N:
             r._eng = _lib.Engine()
             r.get_sampled_points(p.X_domain, p.X_boundary)
             r.shard(virtual_ranks=1)
-            r.Gram_matrix("Gaussian", 0.2, ng, "adaptive")
-            r.Gram_Cholesky()
-            var["right_looking_NB512"] = int(r.chol_info)
+            # right-looking (sharded schedule, one rank): K = NB products per update; 'blocksum' sums them from zero and
+            # subtracts once (what LAPACK's GEMM-based updates do) instead of entry-by-entry progressive subtraction
+            for nb in (128, 256, 512):
+                for bsum in (0, 1):
+                    r._eng.set_option("NB", nb)
+                    r._eng.set_option("blocksum", bsum)
+                    r.Gram_matrix("Gaussian", 0.2, ng, "adaptive")
+                    r.Gram_Cholesky()
+                    var[f"right_looking_NB{nb}_{'blocksum' if bsum else 'progressive'}"] = int(r.chol_info)
             r._eng.close()
             rec["gpu_info_other_schedules"] = var
         rec["verdict"] = ("both fail: indefinite in FP64" if rec.get("lapack_dpotrf_info", 0) > 0 and rec["gpu_info"] > 0 else
