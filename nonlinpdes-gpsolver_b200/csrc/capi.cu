@@ -127,6 +127,7 @@ int gpp_destroy(gpp_handle* h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   if (h->dist) gpp_dist_finalize(h);       // NCCL communicator + the distributed buffers
+  dist_local_release(h);
   dev_free(h->Xd); dev_free(h->Xb); dev_free(h->Xall);
   for (auto& s : h->slot) { dev_free(s.T); dev_free(s.udiag); dev_free(s.Ainv); }
   GnState& g = h->gn;
@@ -162,6 +163,7 @@ int gpp_set_option(gpp_handle* h, const char* name, double value) {
   if (!strcmp(name, "tiled_max_n")) { h->tiled_max_n = (int)value; return GPP_OK; }
   if (!strcmp(name, "tiled_grid_limit")) { h->tiled_grid_limit = (int)value; return GPP_OK; }
   if (!strcmp(name, "blocksum")) { h->blocksum = value != 0.0; return GPP_OK; }
+  if (!strcmp(name, "rl_potrf")) { h->rl_potrf = value != 0.0; return GPP_OK; }
   if (!strcmp(name, "fused_trsm_rows")) { h->fused_trsm_rows = (int)value; return GPP_OK; }
   if (!strcmp(name, "gemm_tile")) {
     const int t = (int)value;
@@ -322,7 +324,10 @@ int gpp_potrf(gpp_handle* h, int slot, int* info) {
   CUDA_TRY(h, cudaSetDevice(h->device));
   GramSlot& s = h->slot[slot];
   if (s.factored) { h->err = "already factored"; return -3; }
-  int rc = potrf_lower(h, s.T, s.ld, s.M, &s.mapT);
+  // large slots: right-looking schedule with block summation (robust at nuggets ~1e-13, see gpp_internal.cuh);
+  // small ones: the persistent tiled kernel inside potrf_lower
+  int rc = (h->rl_potrf && s.M > h->tiled_max_n) ? potrf_right_looking(h, s.T, s.ld, s.M, &s.mapT)
+                                                  : potrf_lower(h, s.T, s.ld, s.M, &s.mapT);
   if (rc) return rc;
   int hinfo = 0;
   CUDA_TRY(h, cudaMemcpyAsync(&hinfo, h->d_info, sizeof(int), cudaMemcpyDeviceToHost, h->stream));

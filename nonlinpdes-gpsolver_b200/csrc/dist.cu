@@ -471,6 +471,7 @@ int bcast_diag(gpp_handle* h, DistState* d, double* X, long ld, int n, int NB, i
 }
 
 int ensure_staging(gpp_handle* h, DistState* d, int n, int NB) {
+  if (d->world <= 1) return GPP_OK;       // nothing travels
   const int nblk = nblocks_of(n, NB);
   int rc = dev_reserve(h, &d->gbuf, (size_t)(nblk + d->P) * NB * NB);
   if (rc) return rc;
@@ -912,6 +913,30 @@ int dist_ablocks(gpp_handle* h, DistState* d, GramSlot& s) {
 }
 
 }  // namespace
+
+int potrf_right_looking(gpp_handle* h, double* A, long ld, int n, const TMap2* map) {
+  if (!h->dist_local) {
+    DistState* d = new DistState();
+    d->rank = 0; d->world = 1; d->nv = 0; d->P = 1; d->Q = 1;
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    CUDA_TRY(h, cudaStreamCreateWithPriority(&d->sC, cudaStreamNonBlocking, hi));
+    h->dist_local = d;
+  }
+  return dist_potrf_matrix(h, static_cast<DistState*>(h->dist_local), A, ld, n, map, 0, false, nullptr, 0);
+}
+
+void dist_local_release(gpp_handle* h) {
+  if (!h->dist_local) return;
+  DistState* d = static_cast<DistState*>(h->dist_local);
+  for (auto& kv : d->plans) {
+    if (kv.second.dev) cudaFree(kv.second.dev);
+    if (kv.second.dev_hblocks) cudaFree(kv.second.dev_hblocks);
+  }
+  if (d->sC) cudaStreamDestroy(d->sC);
+  delete d;
+  h->dist_local = nullptr;
+}
 
 // Hessian blocks of the own (bi, bc) pairs + distributed Cholesky of H; called from gn_step when h->dist_gn
 int dist_gn_hess_potrf(gpp_handle* h) {

@@ -115,8 +115,13 @@ struct gpp_handle {
   int tiled_potrf = 1;        // use the persistent tiled kernel for diagonal blocks and small matrices
   int tiled_max_n = 4608;     // largest matrix factored whole by the tiled kernel
   int tiled_grid_limit = 0;   // tests / tuning: cap on its grid size (0 = resident capacity)
-  int blocksum = 0;           // task-list updates: 1 = sum the K = NB products of a launch from zero, then subtract once
-                              // (LAPACK-style block summation) instead of the entry-by-entry progressive order
+  int blocksum = 1;           // task-list updates (right-looking schedules): 1 = sum the K = NB products of a launch from zero and
+                              // subtract once (block summation, what LAPACK's GEMM-based updates do); 0 = entry-by-entry
+                              // progressive subtraction.  Measured (profiles/r02_nugget_*.jsonl): at N_domain = 20 000, nugget 1e-13
+                              // every progressive schedule breaks down near pivot 35 000, block summation (NB 128 / 256 / 512) does not
+  int rl_potrf = 1;           // Cholesky of a Gram slot larger than tiled_max_n: right-looking task-list schedule (block summation)
+                              // instead of the left-looking long-K schedule (progressive)
+  void* dist_local = nullptr; // one-rank instance of the sharded scheduler used by the single-GPU right-looking factorisation
   int fused_trsm_rows = 65536; // sharded path: panels with at most this many own rows use the one-launch panel solve
   double* work = nullptr;     // scratch (panel copies)
   size_t work_bytes = 0;
@@ -266,6 +271,9 @@ int gn_grad(gpp_handle* h);           // t = L^{-T} s and the gradient
 // multi-GPU (elliptic): H blocks listed in d_blocks (int4: bi, bc, index of the 2 x 2 group of A sub-blocks, unused) from
 // the compact sub-block store Asub (blocks of nbh x nbh, leading dimension nbh, order (p, p') = 00, 01, 10, 11)
 int dist_gn_hess_potrf(gpp_handle* h);   // dist.cu
+// single GPU: the right-looking schedule of the sharded path with one rank (task-list updates, look-ahead streams)
+int potrf_right_looking(gpp_handle* h, double* A, long ld, int n, const TMap2* map);
+void dist_local_release(gpp_handle* h);
 int gn_hess_blocks(gpp_handle* h, const int4* d_blocks, int nblocks, const double* Asub, int nbh);
 int gram_kernel_eval(gpp_handle* h, int kernel, const double* kparams, int opx, int opy, const double* d_in, long n,
                      double* d_out);
