@@ -170,6 +170,20 @@ class _GPProblem(object):
         eng = self._engine()
         eng.timer_start()
         self.chol_info = eng.dist_potrf() if self._sharded else eng.potrf(0)
+        self.chol_schedule = 'right-looking, block summation (sharded)' if self._sharded else 'default'
+        if self.chol_info > 0 and not self._sharded and eng.gram_size(0)[0] > 4608:
+            # the fast left-looking schedule subtracts entry by entry; near the edge of FP64 (nugget ~1e-13, N_domain >= 20 000)
+            # the right-looking schedule with block summation still factors (profiles/r02_nugget_*.jsonl): rebuild Theta, retry
+            eng.gram_assemble(0, self._eqn, self.kernel, self.kernel_parameter)
+            if self._nugget_add is not None:
+                eng.gram_add_diag(0, self._nugget_add)
+            eng.set_option("rl_potrf", 1)
+            try:
+                info = eng.potrf(0)
+            finally:
+                eng.set_option("rl_potrf", 0)
+            if info == 0:
+                self.chol_info, self.chol_schedule = 0, 'right-looking, block summation (retry after a failed pivot)'
         self.timings['potrf_ms'] = eng.timer_stop()
         self._inverted = False
         self._state = 'chol'

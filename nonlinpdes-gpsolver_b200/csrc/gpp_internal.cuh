@@ -119,8 +119,10 @@ struct gpp_handle {
                               // subtract once (block summation, what LAPACK's GEMM-based updates do); 0 = entry-by-entry
                               // progressive subtraction.  Measured (profiles/r02_nugget_*.jsonl): at N_domain = 20 000, nugget 1e-13
                               // every progressive schedule breaks down near pivot 35 000, block summation (NB 128 / 256 / 512) does not
-  int rl_potrf = 1;           // Cholesky of a Gram slot larger than tiled_max_n: right-looking task-list schedule (block summation)
-                              // instead of the left-looking long-K schedule (progressive)
+  int rl_potrf = 0;           // Cholesky of a Gram slot larger than tiled_max_n: 1 = right-looking task-list schedule (block summation,
+                              // factors N_domain = 20 000 at nugget 1e-13 where the progressive schedules break down) instead of the
+                              // left-looking long-K schedule (15 % faster on one GPU: 5.15 s against 5.94 s at N_domain = 40 000).
+                              // The Python classes retry with it automatically when the fast schedule reports a failed pivot.
   void* dist_local = nullptr; // one-rank instance of the sharded scheduler used by the single-GPU right-looking factorisation
   int fused_trsm_rows = 65536; // sharded path: panels with at most this many own rows use the one-launch panel solve
   double* work = nullptr;     // scratch (panel copies)

@@ -406,3 +406,22 @@ def test_full_size_solve_properties(pkg):
     Xt = np.random.uniform(0, 1, (500, 2))
     p.extend_sol(Xt)
     assert np.max(np.abs(p.extended_sol - o.elliptic_u(Xt[:, 0], Xt[:, 1]))) < 1e-4
+
+
+def test_factorisation_retry_at_the_edge_of_fp64(pkg):
+    """N_domain = 20 000 (M = 40 572) at the BASELINE nugget 1e-13: every schedule that subtracts the updates entry by entry breaks
+    down near pivot 35 000 while LAPACK dpotrf factors the same matrix (profiles/r02_nugget_variants_N20k.jsonl); the
+    right-looking schedule with block summation factors it too.  Gram_Cholesky() retries with that schedule on its own."""
+    import math
+    np.random.seed(0)
+    N = 20000
+    p = pkg["PDEs"].Nonlinear_elliptic2d(alpha=1.0, m=3, bdy=o.elliptic_u, rhs=o.elliptic_f)
+    p.sampled_pts(N, 4 * (math.ceil(math.sqrt(N)) + 1))
+    p.Gram_matrix("Gaussian", 0.2, 1e-13, "adaptive")
+    p.Gram_Cholesky()
+    assert p.chol_info == 0
+    assert "retry" in p.chol_schedule
+    # the factor is usable: L (L^T x) reproduces a right-hand side through the two vector solves
+    rng = np.random.RandomState(0)
+    x = rng.standard_normal(2 * N + p.N_boundary)
+    assert np.all(np.isfinite(p._engine().solve_vec(0, x)))
