@@ -117,6 +117,10 @@ int gpp_dist_init_virtual(gpp_handle* h, int nranks);
 /* process grid, P * Q = number of ranks; block (bi, bc) belongs to rank (bi mod P) * Q + (bc mod Q) */
 int gpp_dist_set_grid(gpp_handle* h, int P, int Q);
 int gpp_dist_info(gpp_handle* h, int* rank, int* world, int* P, int* Q);
+/* host-only self-check of the owner-computes task plans for an n x n matrix on a P x Q grid (no GPU needed): every block
+ * that a step must solve / update is handled by exactly one rank, its owner.  phase 0 Cholesky, 1 U = L^-T, 2 Theta^-1
+ * sub-blocks (n = N_domain, nb_extra = boundary rows).  0 = consistent. */
+int gpp_dist_plan_check(int n, int NB, int P, int Q, int phase, int nb_extra);
 /* how finished panels travel: 1 = peer-to-peer (the solve kernels store every finished tile straight into the peers'
  * replicated buffers over NVLink through CUDA IPC mappings and announce it by flags), 0 = NCCL all-gather / broadcast
  * (GPP_DIST_P2P=0, or CUDA IPC unavailable) */

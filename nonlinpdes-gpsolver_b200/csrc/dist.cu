@@ -1042,6 +1042,72 @@ int gpp_dist_info(gpp_handle* h, int* rank, int* world, int* P, int* Q) {
   return GPP_OK;
 }
 
+// Host-only consistency check of the task plans (no GPU, no handle): builds the plans of all P * Q ranks for an n x n
+// matrix with block size NB and verifies, for every step, that each block that must be touched is touched by exactly one
+// rank (its owner) -- panel blocks solved once, trailing blocks updated once, Hessian blocks owned once.
+// phase: 0 = right-looking Cholesky, 1 = U = L^{-T}, 2 = Theta^{-1} sub-blocks (n = N_domain, M = 2 n + nb_extra).
+// Returns 0, or a positive code identifying the first violated property.
+int gpp_dist_plan_check(int n, int NB, int P, int Q, int phase, int nb_extra) {
+  if (n <= 0 || NB <= 0 || NB % 64 || P < 1 || Q < 1 || P * Q > 64 || phase < 0 || phase > 2) return -1;
+  const int nblk = nblocks_of(n, NB);
+  std::vector<Plan> plans(P * Q);
+  std::vector<Grid> grids;
+  for (int r = 0; r < P * Q; ++r) grids.push_back(Grid{P, Q, r / Q, r % Q});
+  const int off[3] = {0, n, 2 * n};
+  for (int r = 0; r < P * Q; ++r) {
+    if (phase == 0) build_potrf_plan(plans[r], grids[r], n, NB);
+    else if (phase == 1) build_uinv_plan(plans[r], grids[r], n, NB);
+    else build_ablock_plan(plans[r], grids[r], n, 2 * n + nb_extra, off, NB);
+  }
+  if (phase == 2) {
+    std::vector<int> cnt((size_t)nblk * nblk, 0);
+    for (int r = 0; r < P * Q; ++r) {
+      if (plans[r].host.size() != 4 * plans[r].hblocks.size()) return 20;
+      for (const int4& hb : plans[r].hblocks) {
+        if (owner_of(grids[r], hb.x, hb.y) != r || hb.y > hb.x) return 21;
+        cnt[(size_t)hb.x * nblk + hb.y]++;
+      }
+    }
+    for (int bi = 0; bi < nblk; ++bi)
+      for (int bc = 0; bc <= bi; ++bc)
+        if (cnt[(size_t)bi * nblk + bc] != 1) return 22;
+    return 0;
+  }
+  for (int j = 0; j < nblk; ++j) {
+    std::vector<int> upd((size_t)nblk * nblk, 0), solved(nblk, 0);
+    for (int r = 0; r < P * Q; ++r) {
+      const Plan& pl = plans[r];
+      // panel rows of this rank: block-cyclic arithmetic map
+      const TrsmRows& rm = pl.rows[j];
+      for (int lr = 0; lr < rm.rows; lr += NB) {
+        const int b = rm.first_blk + (lr / NB) * rm.stride_blk;
+        if (b < 0 || b >= nblk) return 10;
+        if (owner_of(grids[r], b, j) != r) return 11;
+        solved[b]++;
+      }
+      for (const Launch* l : {&pl.la[j], &pl.bulkA[j], &pl.bulkB[j]})
+        for (int t = 0; t < l->count; ++t) {
+          const GemmTask& g = pl.host[l->off + t];
+          const int bi = g.c_row / NB, bc = g.c_col / NB;
+          if (owner_of(grids[r], bi, bc) != r) return 12;
+          if (g.k0 != j * NB || g.k1 != j * NB + rows_of(n, NB, j)) return 13;
+          if (g.m != rows_of(n, NB, bi) || g.n != rows_of(n, NB, bc)) return 14;
+          upd[(size_t)bi * nblk + bc]++;
+        }
+    }
+    for (int b = 0; b < nblk; ++b) {
+      const bool want = phase == 0 ? (b > j) : (b <= j);       // Cholesky: blocks below the diagonal; U: rows up to the diagonal
+      if (solved[b] != (want ? 1 : 0)) return 15;
+    }
+    for (int bi = 0; bi < nblk; ++bi)
+      for (int bc = 0; bc < nblk; ++bc) {
+        const bool want = phase == 0 ? (bc > j && bc <= bi) : (bi <= j && bc > j);
+        if (upd[(size_t)bi * nblk + bc] != (want ? 1 : 0)) return 16;
+      }
+  }
+  return 0;
+}
+
 int gpp_dist_exchange_mode(gpp_handle* h) {
   if (!h || !h->dist) return -1;
   return use_p2p(ds(h)) ? 1 : 0;

@@ -39,6 +39,19 @@ def test_block_ownership_maps():
         _dist.grid_shape(8, 3)
 
 
+def test_task_plans_are_consistent_on_the_host():
+    """The real plan builder of csrc/dist.cu, run on the CPU through the C ABI (no GPU): for every step of the sharded
+    Cholesky and of U = L^-T each block is solved / updated by exactly one rank -- its owner -- with the right K range and
+    extents; every Hessian block has exactly one owner with its four Theta^-1 sub-block tasks."""
+    from nonlinpdes_gpsolver_b200 import _lib
+    for (n, NB) in ((1300, 128), (2048, 256), (5000, 512), (700, 128)):
+        for (P, Q) in ((1, 1), (2, 1), (3, 1), (2, 2), (8, 1), (2, 4), (4, 2), (1, 8)):
+            for phase in (0, 1):
+                assert _lib.dist_plan_check(n, NB, P, Q, phase) == 0, (n, NB, P, Q, phase)
+            assert _lib.dist_plan_check(n, NB, P, Q, 2, nb_extra=96) == 0, (n, NB, P, Q)
+    assert _lib.dist_plan_check(1000, 100, 2, 1, 0) == -1            # block size must be a multiple of 64
+
+
 _GLOO_WORKER = r'''
 import os, sys
 sys.path.insert(0, os.environ["GPP_ROOT"])
