@@ -139,7 +139,8 @@ class Engine:
         la = os.environ.get("GPP_LOOKAHEAD")
         if la is not None:
             self.set_option("lookahead", float(la))
-        for env, opt in (("GPP_BLOCKSUM", "blocksum"), ("GPP_RL_POTRF", "rl_potrf"), ("GPP_TILED_POTRF", "tiled_potrf")):
+        for env, opt in (("GPP_BLOCKSUM", "blocksum"), ("GPP_RL_POTRF", "rl_potrf"), ("GPP_TILED_POTRF", "tiled_potrf"),
+                         ("GPP_PERSISTENT_GEMM", "persistent_gemm")):
             v = os.environ.get(env)
             if v is not None:
                 self.set_option(opt, float(v))

@@ -162,6 +162,7 @@ int gpp_set_option(gpp_handle* h, const char* name, double value) {
   if (!strcmp(name, "tiled_potrf")) { h->tiled_potrf = value != 0.0; return GPP_OK; }
   if (!strcmp(name, "tiled_max_n")) { h->tiled_max_n = (int)value; return GPP_OK; }
   if (!strcmp(name, "tiled_grid_limit")) { h->tiled_grid_limit = (int)value; return GPP_OK; }
+  if (!strcmp(name, "persistent_gemm")) { h->persistent_gemm = value != 0.0; return GPP_OK; }
   if (!strcmp(name, "blocksum")) { h->blocksum = value != 0.0; return GPP_OK; }
   if (!strcmp(name, "rl_potrf")) { h->rl_potrf = value != 0.0; return GPP_OK; }
   if (!strcmp(name, "fused_trsm_rows")) { h->fused_trsm_rows = (int)value; return GPP_OK; }

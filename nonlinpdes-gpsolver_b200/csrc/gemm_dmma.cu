@@ -278,6 +278,137 @@ gemm_nt_dmma_kernel(const __grid_constant__ GemmParams p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Persistent task-list variant (right-looking schedules: K = NB per task, thousands of tiles per launch).  ncu on the
+// one-CTA-per-tile launch (profiles/r02_ncu_task_gemm_bulk_raw.csv): DMMA pipe active 83 % of the SM-active cycles against
+// 95 % for the long-K launches -- ~13 us of launch, task fetch, barrier set-up, pipeline fill and epilogue per 65 us tile.
+// Here a CTA stays on its SM and walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the mbarrier ring keeps running
+// across tiles, so the producer warp is already fetching the next tile's operands while the consumer warps store the
+// current one.  Same k order per output element as the one-shot kernel.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int TILE>
+__global__ void __launch_bounds__(Cfg<TILE>::THREADS, Cfg<TILE>::MIN_CTAS)
+gemm_tasks_persistent_kernel(const __grid_constant__ GemmParams p, int total_tiles) {
+  constexpr int BM = TILE, BN = TILE;
+  constexpr int CONSUMER_WARPS = Cfg<TILE>::CONSUMER_WARPS, WG = Cfg<TILE>::WG;
+  constexpr int TILE_BYTES = Cfg<TILE>::TILE_BYTES, STAGE_BYTES = Cfg<TILE>::STAGE_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CONSUMER_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int per = p.task_tps * p.task_tps;
+  uint32_t cbase = 0;                  // chunks consumed by this CTA before the current tile (same count in every warp)
+
+  const int wm = warp / WG, wn = warp % WG;
+  const int g = lane >> 2, t = lane & 3;
+  uint32_t koff[4];
+#pragma unroll
+  for (int s = 0; s < 4; ++s) koff[s] = ((((s + 4 * (t >> 1)) ^ g) << 4) + ((t & 1) << 3));
+  const uint32_t a_thr = (wm * 32 + g) * 128;
+  const uint32_t b_thr = (wn * 32 + g) * 128;
+  const uint32_t smem_base = smem_u32(smem);
+
+  for (int tile_id = blockIdx.x; tile_id < total_tiles; tile_id += gridDim.x) {
+    const int4* tp = reinterpret_cast<const int4*>(p.tasks + tile_id / per);
+    const int4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);   // {a_row, b_row, c_row, c_col} {m, n, k0, k1} {kb_off, tri, -, -}
+    const int tile = tile_id % per;
+    const int ti = tile / p.task_tps, tj = tile % p.task_tps;
+    const int row_base = ti * BM, col_base = tj * BN;
+    if (row_base >= t1.x || col_base >= t1.y || (t2.y && tj > ti)) continue;   // same decision in every warp: no chunks
+    const int a_row = t0.x + row_base, b_row = t0.y + col_base;
+    const int k_lo = t1.z, k_hi = t1.w, kb_off = t2.x;
+    const int nchunks = (k_hi > k_lo) ? (k_hi - k_lo + BK - 1) / BK : 0;
+
+    if (warp == CONSUMER_WARPS) {
+      // ===== TMA producer: runs ahead of the consumers across tile boundaries =====
+      if (lane == 0) {
+        for (int c = 0; c < nchunks; ++c) {
+          const uint32_t gc = cbase + c;
+          const int s = gc % STAGES;
+          const uint32_t ph = (gc / STAGES) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* sa = smem + s * STAGE_BYTES;
+          uint8_t* sb = sa + TILE_BYTES;
+          mbar_expect_tx(&full[s], STAGE_BYTES);
+          const int k = k_lo + c * BK;
+          tma_load_2d(sa, &p.mapA, &full[s], k, a_row);
+          tma_load_2d(sb, &p.mapB, &full[s], k + kb_off, b_row);
+        }
+      }
+      cbase += nchunks;
+      continue;
+    }
+
+    // ===== consumers (block summation: the products of the tile are summed from zero, the addend joins in the epilogue) =====
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int c = 0; c < nchunks; ++c) {
+      const uint32_t gc = cbase + c;
+      const int s = gc % STAGES;
+      const uint32_t ph = (gc / STAGES) & 1;
+      mbar_wait(&full[s], ph);
+      const uint32_t sa = smem_base + s * STAGE_BYTES + a_thr;
+      const uint32_t sb = smem_base + s * STAGE_BYTES + TILE_BYTES + b_thr;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        double a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = lds64(sa + i * 1024 + koff[ks]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b[j] = lds64(sb + j * 1024 + koff[ks]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+    }
+    cbase += nchunks;
+    // ===== epilogue: C = Cin + alpha * acc.  The task is decoded again here (cache hit) so that nothing but the
+    // accumulators and the ring state lives across the main loop (96 registers per thread).
+    {
+      const int4 e0 = __ldg(tp), e1 = __ldg(tp + 1);
+      double* Cp = p.C + (long)e0.z * p.ldc + e0.w;
+      const double* Cinp = p.Cin ? p.Cin + (long)e0.z * p.ldcin + e0.w : nullptr;
+      const int rb = (tile / p.task_tps) * BM + wm * 32 + g, cb = (tile % p.task_tps) * BN + wn * 32 + 2 * t;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = rb + i * 8;
+        if (r >= e1.x) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int cc = cb + j * 8;
+          if (cc >= e1.y) continue;
+          double v0 = p.alpha * acc[i][j][0], v1 = p.alpha * acc[i][j][1];
+          double* dst = Cp + (long)r * p.ldc + cc;
+          const bool two = (cc + 1 < e1.y);
+          if (Cinp) {
+            const double* src = Cinp + (long)r * p.ldcin + cc;
+            v0 += src[0];
+            if (two) v1 += src[1];
+          }
+          if (two && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+            *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
+          } else {
+            dst[0] = v0;
+            if (two) dst[1] = v1;
+          }
+        }
+      }
+    }
+  }
+}
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -372,7 +503,23 @@ int launch_tasks(gpp_handle* h, const GemmTaskDesc& d, GemmParams& p) {
   }
   p.task_tps = d.bs / TILE;
   const long ntiles = (long)d.ntasks * p.task_tps * p.task_tps;
-  gemm_nt_dmma_kernel<TILE><<<(unsigned)ntiles, Cfg<TILE>::THREADS, Cfg<TILE>::SMEM_BYTES, h->cur>>>(p);
+  if (h->persistent_gemm && (p.blocksum || p.Cin == nullptr)) {
+    static bool attr_p[64] = {false};
+    static int sms[64] = {0};
+    if (h->device >= 64 || !attr_p[h->device]) {
+      CUDA_TRY(h, cudaFuncSetAttribute(gemm_tasks_persistent_kernel<TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<TILE>::SMEM_BYTES));
+      int n = 0;
+      CUDA_TRY(h, cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, h->device));
+      if (h->device < 64) { attr_p[h->device] = true; sms[h->device] = n; }
+    }
+    int nsm = h->device < 64 ? sms[h->device] : 148;
+    if (nsm <= 0) nsm = 148;
+    const long cap = (long)nsm * Cfg<TILE>::MIN_CTAS;
+    const unsigned grid = (unsigned)(ntiles < cap ? ntiles : cap);
+    gemm_tasks_persistent_kernel<TILE><<<grid, Cfg<TILE>::THREADS, Cfg<TILE>::SMEM_BYTES, h->cur>>>(p, (int)ntiles);
+  } else {
+    gemm_nt_dmma_kernel<TILE><<<(unsigned)ntiles, Cfg<TILE>::THREADS, Cfg<TILE>::SMEM_BYTES, h->cur>>>(p);
+  }
   h->launches++;
   CUDA_TRY(h, cudaGetLastError());
   return GPP_OK;

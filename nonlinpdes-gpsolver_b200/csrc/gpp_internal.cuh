@@ -124,6 +124,7 @@ struct gpp_handle {
                               // left-looking long-K schedule (15 % faster on one GPU: 5.15 s against 5.94 s at N_domain = 40 000).
                               // The Python classes retry with it automatically when the fast schedule reports a failed pivot.
   void* dist_local = nullptr; // one-rank instance of the sharded scheduler used by the single-GPU right-looking factorisation
+  int persistent_gemm = 1;    // task-list GEMM: CTAs stay resident and walk the tile list (0: one CTA per tile)
   int fused_trsm_rows = 65536; // sharded path: panels with at most this many own rows use the one-launch panel solve
   double* work = nullptr;     // scratch (panel copies)
   size_t work_bytes = 0;
