@@ -378,30 +378,50 @@ gemm_tasks_persistent_kernel(const __grid_constant__ GemmParams p, int total_til
     // accumulators and the ring state lives across the main loop (96 registers per thread).
     {
       const int4 e0 = __ldg(tp), e1 = __ldg(tp + 1);
-      double* Cp = p.C + (long)e0.z * p.ldc + e0.w;
-      const double* Cinp = p.Cin ? p.Cin + (long)e0.z * p.ldcin + e0.w : nullptr;
+      // the addend is read before the same thread overwrites the same element, so for the compiler's purposes the two
+      // pointers do not alias: with __restrict__ it may issue the loads of a row ahead of the stores of the previous one
+      // (ncu source page before this change: 13 % of the samples sat on the 16 serialised load -> add -> store chains)
+      double* __restrict__ Cp = p.C + (long)e0.z * p.ldc + e0.w;
+      const double* __restrict__ Cinp = p.Cin ? p.Cin + (long)e0.z * p.ldcin + e0.w : nullptr;
       const int rb = (tile / p.task_tps) * BM + wm * 32 + g, cb = (tile % p.task_tps) * BN + wn * 32 + 2 * t;
+      const bool interior = (rb + 24 < e1.x) && (cb + 25 < e1.y) && ((reinterpret_cast<uintptr_t>(Cp) & 15) == 0) && !(p.ldc & 1) &&
+                            Cinp && ((reinterpret_cast<uintptr_t>(Cinp) & 15) == 0) && !(p.ldcin & 1);
+      if (interior) {
+        // full tile, 16-byte aligned: four 128-bit addend loads per row in flight, then four 128-bit stores
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int r = rb + i * 8;
-        if (r >= e1.x) continue;
+        for (int i = 0; i < 4; ++i) {
+          const long ro = (long)(rb + i * 8);
+          double2 cin[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int cc = cb + j * 8;
-          if (cc >= e1.y) continue;
-          double v0 = p.alpha * acc[i][j][0], v1 = p.alpha * acc[i][j][1];
-          double* dst = Cp + (long)r * p.ldc + cc;
-          const bool two = (cc + 1 < e1.y);
-          if (Cinp) {
-            const double* src = Cinp + (long)r * p.ldcin + cc;
-            v0 += src[0];
-            if (two) v1 += src[1];
-          }
-          if (two && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-            *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
-          } else {
-            dst[0] = v0;
-            if (two) dst[1] = v1;
+          for (int j = 0; j < 4; ++j) cin[j] = *reinterpret_cast<const double2*>(Cinp + ro * p.ldcin + cb + j * 8);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<double2*>(Cp + ro * p.ldc + cb + j * 8) =
+                make_double2(p.alpha * acc[i][j][0] + cin[j].x, p.alpha * acc[i][j][1] + cin[j].y);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = rb + i * 8;
+          if (r >= e1.x) continue;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int cc = cb + j * 8;
+            if (cc >= e1.y) continue;
+            double v0 = p.alpha * acc[i][j][0], v1 = p.alpha * acc[i][j][1];
+            double* dst = Cp + (long)r * p.ldc + cc;
+            const bool two = (cc + 1 < e1.y);
+            if (Cinp) {
+              const double* src = Cinp + (long)r * p.ldcin + cc;
+              v0 += src[0];
+              if (two) v1 += src[1];
+            }
+            if (two && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+              *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
+            } else {
+              dst[0] = v0;
+              if (two) dst[1] = v1;
+            }
           }
         }
       }
