@@ -124,7 +124,10 @@ struct gpp_handle {
                               // left-looking long-K schedule (15 % faster on one GPU: 5.15 s against 5.94 s at N_domain = 40 000).
                               // The Python classes retry with it automatically when the fast schedule reports a failed pivot.
   void* dist_local = nullptr; // one-rank instance of the sharded scheduler used by the single-GPU right-looking factorisation
-  int persistent_gemm = 1;    // task-list GEMM: CTAs stay resident and walk the tile list (0: one CTA per tile)
+  int persistent_gemm = 0;    // task-list GEMM: 1 = CTAs stay resident and walk the tile list, 0 = one CTA per tile (default).
+                              // Measured (profiles/r02_summary.md): resident CTAs never hand an SM to the high-priority panel chain
+                              // that runs beside the trailing update, so the look-ahead stalls: 3.57 s instead of 2.99 s per
+                              // N_domain = 40 000 solve on 8 GPUs (single GPU, right-looking: no gain either, 28.8 vs 28.9 TFLOP/s)
   int fused_trsm_rows = 65536; // sharded path: panels with at most this many own rows use the one-launch panel solve
   double* work = nullptr;     // scratch (panel copies)
   size_t work_bytes = 0;
