@@ -45,6 +45,14 @@ NCU_GEMM_TRAFFIC = {"bytes_per_launch": 13.385e9 + 0.138e9, "algorithmic_bytes_p
                     "source": "profiles/r01_ncu_summary.md"}
 
 
+# the dominant kernel of the sharded (right-looking) schedules is the same kernel in task-list mode, K = NB = 512:
+# ncu --set full of the step-0 trailing update at N_domain=20000 (3003 block tasks, 48048 CTAs; profiles/r02_ncu_task_gemm_bulk_raw.csv):
+# DRAM 11.83 GB read + 6.10 GB written; algorithmic: every C block read and written once (12.59 GB) + the 166 MB panel once
+NCU_TASK_GEMM_TRAFFIC = {"bytes_per_launch": 11.835e9 + 6.096e9, "algorithmic_bytes_per_launch": 12.59e9 + 0.166e9,
+                         "launch": "gemm_nt_dmma_kernel<128> task-list mode, 3003 blocks of 512x512, K=512 (N_domain=20000, step 0)",
+                         "source": "profiles/r02_summary.md"}
+
+
 def u_true(x1, x2):
     return np.sin(np.pi * x1) * np.sin(np.pi * x2) + 2 * np.sin(4 * np.pi * x1) * np.sin(4 * np.pi * x2)
 
@@ -358,7 +366,7 @@ def main():
             "phases_ms": {"assembly": T_asm, "potrf": T_potrf, "inverse": T_inv, "gn_total": T_gn, "gn_per_step": T_gn / a.gn_steps},
             "roofline": {"kernel": "gemm_nt_dmma_kernel (potrf + inverse phases, M^3 algorithmic flops, aggregate over the GPUs)",
                          "bound": "tensor", "achieved": gemm_tf, "peak": fp64_peak * world, "unit": "TFLOP/s", "frac": gemm_tf / (fp64_peak * world),
-                         "traffic": NCU_GEMM_TRAFFIC, "peak_source": fp64_how + (f" x {world} GPUs" if world > 1 else ""),
+                         "traffic": NCU_GEMM_TRAFFIC if world == 1 else NCU_TASK_GEMM_TRAFFIC, "peak_source": fp64_how + (f" x {world} GPUs" if world > 1 else ""),
                          "potrf_tflops": potrf_tf, "potrf_frac": potrf_tf / (fp64_peak * world),
                          "inverse_tflops": 2 * M ** 3 / 3.0 / T_inv / 1e9},
             "assembly_roofline": {"kernel": "gram_assemble_kernel" if world == 1 else "gram_rows_kernel (row-sharded)", "bound": "hbm",
