@@ -124,6 +124,41 @@ class FakeEngine:
             return F[1] if slot == 0 else F[0]
         return F
 
+    # ---- options / the sharded call surface (one fake "rank": same numbers as the single-device calls)
+    def set_option(self, name, value):
+        self.calls.append(f"set_option[{name}]")
+
+    def dist_init_virtual(self, nranks):
+        self.world, self.rank = int(nranks), 0
+        self.calls.append(f"dist_init_virtual[{nranks}]")
+
+    def dist_set_grid(self, P, Q):
+        self.grid = (int(P), int(Q))
+
+    def dist_info(self):
+        return dict(rank=0, world=self.world, P=self.grid[0], Q=self.grid[1])
+
+    def dist_gram_assemble(self, layout, kernel, kernel_parameter):
+        self.gram_assemble(0, layout, kernel, kernel_parameter)
+        self.calls.append("dist_gram_assemble")
+
+    def dist_get_diag(self):
+        return self.gram_get_diag(0)
+
+    def dist_add_diag(self, add):
+        self.gram_add_diag(0, add)
+
+    def dist_potrf(self):
+        self.calls.append("dist_potrf")
+        return self.potrf(0)
+
+    def dist_inverse(self):
+        self.calls.append("dist_inverse")
+
+    def dist_gn_step(self, step):
+        self.calls.append("dist_gn_step")
+        return self.gn_step(step)
+
     # ---- prediction
     def predict(self, slot, X_test, w):
         s = self.slots[slot]

@@ -160,3 +160,32 @@ def test_facade_end_to_end_on_fake_engine(fake, capsys):
     # user-supplied points (the upstream get_sample bug is fixed)
     s.get_sample(s.eqn.X_domain.copy(), s.eqn.X_boundary.copy(), print_option=False)
     assert s.eqn.N_domain == 50
+
+
+def test_sharded_class_flow_on_fake_engine(fake):
+    """PDEs.shard(): the problem class routes assembly, nugget, factorisation, inverse and GN steps through the dist_* calls
+    (and only those), keeps the reference's RNG order, and produces the oracle's numbers; other PDEs refuse to shard."""
+    from nonlinpdes_gpsolver_b200 import PDEs
+    N, Nb, steps, seed = 50, 16, 2, 11
+    np.random.seed(seed)
+    p = PDEs.Nonlinear_elliptic2d(alpha=1.0, m=3, bdy=o.elliptic_u, rhs=o.elliptic_f, domain=DOM)
+    p.sampled_pts(N, Nb)
+    assert p.shard(virtual_ranks=4, Q=2) is p
+    assert p._engine().dist_info() == dict(rank=0, world=4, P=2, Q=2)
+    p.Gram_matrix("Gaussian", 0.2, 1e-6, "adaptive")
+    p.Gram_Cholesky()
+    p.GN_method(steps, 1, "rdm", print_hist=False)
+    calls = p._engine().calls
+    assert "dist_gram_assemble" in calls and "dist_potrf" in calls and "dist_inverse" in calls and calls.count("dist_gn_step") == steps
+    assert not any(c.startswith("inverse[") for c in calls)
+    np.random.seed(seed)
+    Xd, Xb = o.sampled_pts_rdm(N, Nb, DOM)
+    init = np.random.normal(0.0, 1.0, N)
+    ref = _oracle_run(o.Nonlinear_elliptic2d(1.0, 3), Xd, Xb, p.rhs_f, p.bdy_g, "Gaussian", 0.2, 1e-6, steps, init)
+    assert np.array_equal(p.init_sol, init) and p.ratio == ref.ratio
+    np.testing.assert_allclose(p.loss_hist, ref.loss_hist, rtol=1e-9)
+    assert np.array_equal(p.Theta, ref.Theta)                       # re-assembled on a scratch handle in sharded mode
+    with pytest.raises(NotImplementedError):
+        p.Hessian_GN(p.sol, p.sol)                                  # no dense read-outs of a sharded problem
+    with pytest.raises(NotImplementedError):
+        PDEs.Eikonal(eps=0.1, bdy=lambda a, b: 0, rhs=lambda a, b: 1).shard(virtual_ranks=2)
